@@ -1,0 +1,773 @@
+// bm25_capi.cu -- host side of libbm25_b200.so: the C ABI declared in include/bm25_b200.h.
+// Owns the HBM-resident index, the per-handle workspace (no cudaMalloc on the steady-state search
+// path) and the launch logic of the kernels in bm25_kernels.cuh.
+#include "../../include/bm25_b200.h"
+#include "bm25_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace bm25;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(e__ == cudaErrorMemoryAllocation ? BM25_ERR_OOM : BM25_ERR_CUDA,      \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__,    \
+                        __LINE__);                                                            \
+    } while (0)
+
+int next_pow2(int64_t x) {
+    int p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    int reserve(size_t n) {
+        if (n <= cap) return BM25_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(BM25_ERR_OOM, "cudaMalloc of %zu bytes failed: %s", want * sizeof(T),
+                        cudaGetErrorString(e));
+        }
+        cap = want;
+        return BM25_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    size_t bytes() const { return cap * sizeof(T); }
+};
+
+template <typename T>
+struct PinnedBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return BM25_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(BM25_ERR_OOM, "cudaMallocHost of %zu bytes failed: %s", want * sizeof(T),
+                        cudaGetErrorString(e));
+        }
+        cap = want;
+        return BM25_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+int check_device(int device, cudaDeviceProp* prop) {
+    static std::mutex mu;
+    static cudaDeviceProp cache[64];
+    static bool cached[64] = {false};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (device >= 0 && device < 64 && cached[device]) {
+            *prop = cache[device];
+            return BM25_OK;
+        }
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(BM25_ERR_NO_DEVICE,
+                    "no CUDA device available (%s); libbm25_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count)
+        return fail(BM25_ERR_INVALID, "device %d out of range (have %d)", device, count);
+    CU(cudaGetDeviceProperties(prop, device));
+    if (prop->major < 10)
+        return fail(BM25_ERR_NO_DEVICE,
+                    "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop->major, prop->minor);
+    if (device < 64) {
+        std::lock_guard<std::mutex> lock(mu);
+        cache[device] = *prop;
+        cached[device] = true;
+    }
+    return BM25_OK;
+}
+
+}  // namespace
+
+struct bm25_index {
+    int device = 0;
+    int sm_count = 148;
+    int64_t n_terms = 0, n_docs = 0, nnz = 0, doc_id_base = 0;
+    bool all_positive = false, was_sorted = true, borrowed = false;
+    int32_t* d_indptr = nullptr;
+    int32_t* d_ids = nullptr;
+    float* d_w = nullptr;
+    std::vector<int32_t> h_indptr;  // host copy for byte accounting / validation
+    // options (0 = auto)
+    int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
+    bool ev_valid = false;
+    // workspace
+    std::mutex mu;
+    DevBuf<int32_t> ws_seg;
+    DevBuf<u64> ws_partial;
+    DevBuf<int32_t> ws_queries, ws_out_ids;
+    DevBuf<float> ws_out_scores;
+    PinnedBuf<int32_t> pin_queries, pin_out_ids;
+    PinnedBuf<float> pin_out_scores;
+    cudaStream_t own_stream = nullptr;
+    size_t smem_optin = 0;
+
+    int tile_docs() const {
+        int t = opt_tile_docs > 0 ? opt_tile_docs : 16384;
+        int64_t need = ((n_docs + kChunk - 1) / kChunk) * kChunk;
+        if (need < t) t = (int)std::max<int64_t>(need, kChunk);
+        t = ((t + kChunk - 1) / kChunk) * kChunk;
+        return t;
+    }
+    int n_tiles() const { return (int)std::max<int64_t>(1, (n_docs + tile_docs() - 1) / tile_docs()); }
+    int64_t device_bytes() const {
+        int64_t b = 0;
+        if (!borrowed) b += (n_terms + 1) * 4 + nnz * 8;
+        b += ws_seg.bytes() + ws_partial.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
+             ws_out_scores.bytes();
+        return b;
+    }
+};
+
+namespace {
+
+int finish_create(bm25_index* ix, const cudaDeviceProp& prop) {
+    ix->sm_count = prop.multiProcessorCount;
+    ix->smem_optin = prop.sharedMemPerBlockOptin;
+    CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
+    return BM25_OK;
+}
+
+// Host-side canonicalisation: returns false if any column needed sorting / merging.
+int canonicalise_host(const int32_t* indptr, const int32_t* indices, const float* data, int64_t n_terms,
+                      int64_t n_docs, int64_t nnz, std::vector<int32_t>& o_ptr,
+                      std::vector<int32_t>& o_idx, std::vector<float>& o_dat, bool* was_sorted,
+                      bool* all_positive) {
+    if (indptr[0] != 0) return fail(BM25_ERR_INVALID, "indptr[0] must be 0 (got %d)", indptr[0]);
+    if (indptr[n_terms] != nnz)
+        return fail(BM25_ERR_INVALID, "indptr[n_terms] (%d) != nnz (%lld)", indptr[n_terms], (long long)nnz);
+    bool sorted = true, positive = true;
+    for (int64_t t = 0; t < n_terms; ++t) {
+        const int64_t s = indptr[t], e = indptr[t + 1];
+        if (e < s) return fail(BM25_ERR_INVALID, "indptr is not monotone at term %lld", (long long)t);
+        for (int64_t p = s; p < e; ++p) {
+            const int32_t d = indices[p];
+            if (d < 0 || d >= n_docs)
+                return fail(BM25_ERR_INVALID, "doc id %d of posting %lld is outside [0, %lld)", d,
+                            (long long)p, (long long)n_docs);
+            const float x = data[p];
+            if (!std::isfinite(x))
+                return fail(BM25_ERR_INVALID, "weight of posting %lld is not finite", (long long)p);
+            if (!(x > 0.f)) positive = false;
+            if (p > s && d <= indices[p - 1]) sorted = false;
+        }
+    }
+    *was_sorted = sorted;
+    *all_positive = positive;
+    if (sorted) return BM25_OK;
+    // sort each column by doc id (stable) and merge duplicate rows by summing in original order
+    o_ptr.assign(n_terms + 1, 0);
+    o_idx.clear();
+    o_dat.clear();
+    o_idx.reserve(nnz);
+    o_dat.reserve(nnz);
+    std::vector<int64_t> perm;
+    for (int64_t t = 0; t < n_terms; ++t) {
+        const int64_t s = indptr[t], e = indptr[t + 1];
+        perm.resize(e - s);
+        std::iota(perm.begin(), perm.end(), s);
+        std::stable_sort(perm.begin(), perm.end(),
+                         [&](int64_t a, int64_t b) { return indices[a] < indices[b]; });
+        for (size_t i = 0; i < perm.size(); ++i) {
+            const int32_t d = indices[perm[i]];
+            const float x = data[perm[i]];
+            if (!o_idx.empty() && (int64_t)o_idx.size() > o_ptr[t] && o_idx.back() == d)
+                o_dat.back() += x;
+            else {
+                o_idx.push_back(d);
+                o_dat.push_back(x);
+            }
+        }
+        o_ptr[t + 1] = (int32_t)o_idx.size();
+    }
+    for (float x : o_dat)
+        if (!(x > 0.f)) positive = false;
+    *all_positive = positive;
+    return BM25_OK;
+}
+
+struct LaunchPlan {
+    int tile_docs, n_tiles, splits, tiles_per_split, cap;
+    size_t smem;
+    u64 theta0;
+};
+
+int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, bool dense, LaunchPlan* lp) {
+    lp->tile_docs = ix->tile_docs();
+    lp->n_tiles = ix->n_tiles();
+    lp->cap = dense ? 0 : next_pow2((int64_t)k + kChunk);
+    // shrink the tile until the CTA fits into shared memory
+    for (;;) {
+        lp->smem = (size_t)lp->tile_docs * 4 + (size_t)lp->cap * 8 + (size_t)T * 8 + 16;
+        if (lp->smem <= ix->smem_optin - 1024) break;
+        if (lp->tile_docs <= kChunk)
+            return fail(BM25_ERR_UNSUPPORTED, "query shape (T=%lld, k=%d) does not fit in shared memory",
+                        (long long)T, k);
+        lp->tile_docs -= kChunk;
+        lp->n_tiles = (int)((ix->n_docs + lp->tile_docs - 1) / lp->tile_docs);
+    }
+    int splits = ix->opt_splits;
+    if (splits <= 0) {
+        const int64_t slots = (int64_t)ix->sm_count * 2 * 4;
+        splits = (int)std::max<int64_t>(1, (slots + Q - 1) / std::max<int64_t>(Q, 1));
+    }
+    if (dense) splits = std::min(splits, lp->n_tiles);
+    splits = std::max(1, std::min(splits, lp->n_tiles));
+    lp->tiles_per_split = (lp->n_tiles + splits - 1) / splits;
+    lp->splits = (lp->n_tiles + lp->tiles_per_split - 1) / lp->tiles_per_split;
+    const bool positive = ix->all_positive && !ix->opt_force_general;
+    // positive index: only strictly positive scores compete, zero-score docs are filled in by
+    // k_merge; general index: every document competes (theta0 = 0 admits all keys).
+    lp->theta0 = positive ? make_key(0.0f, 0u) : 0ull;
+    return BM25_OK;
+}
+
+template <bool kDense>
+int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int64_t Q, cudaStream_t st) {
+    static thread_local size_t configured[64] = {0};
+    auto kern = k_score_topk<kDense>;
+    if (configured[ix->device % 64] < lp.smem) {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ix->smem_optin)));
+        configured[ix->device % 64] = ix->smem_optin;
+    }
+    const int64_t grid = Q * lp.splits;
+    if (grid > 0x7fffffffLL) return fail(BM25_ERR_UNSUPPORTED, "grid too large");
+    kern<<<(unsigned)grid, kThreads, lp.smem, st>>>(a);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return BM25_OK;
+}
+
+int launch_segments(bm25_index* ix, const LaunchPlan& lp, const int32_t* d_queries, int64_t Q, int64_t T,
+                    cudaStream_t st) {
+    const int64_t n_qt = Q * T;
+    int rc = ix->ws_seg.reserve((size_t)n_qt * (lp.n_tiles + 1));
+    if (rc) return rc;
+    const int64_t blocks = (n_qt * 32 + 255) / 256;
+    k_segments<<<(unsigned)blocks, 256, 0, st>>>(ix->d_indptr, ix->d_ids, d_queries, n_qt, (int)ix->n_terms,
+                                                 lp.tile_docs, lp.n_tiles, ix->ws_seg.p);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return BM25_OK;
+}
+
+int launch_merge(const MergeArgs& m, int device, size_t smem_optin, cudaStream_t st) {
+    const size_t smem = (size_t)m.P * 8 + (size_t)m.k_out + 16;
+    static thread_local size_t configured[64] = {0};
+    if (smem > 48 * 1024 && configured[device % 64] < smem) {
+        CU(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin));
+        configured[device % 64] = smem_optin;
+    }
+    k_merge<<<(unsigned)m.Q, kThreads, smem, st>>>(m);
+    ++g_launches;
+    CU(cudaGetLastError());
+    return BM25_OK;
+}
+
+int merge_P(int64_t total, int k_out) {
+    if (total <= 8192) return std::max(next_pow2(total), next_pow2(k_out));
+    return std::max(8192, next_pow2(2 * (int64_t)k_out));
+}
+
+int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T, int k, int32_t* d_out_ids,
+                  float* d_out_scores, cudaStream_t st) {
+    LaunchPlan lp;
+    int rc = make_plan(ix, Q, T, k, false, &lp);
+    if (rc) return rc;
+    if ((rc = ix->ws_partial.reserve((size_t)Q * lp.splits * k))) return rc;
+    const bool timing = ix->opt_timing != 0;
+    if (timing) {
+        for (auto& e : ix->ev)
+            if (!e) CU(cudaEventCreate(&e));
+        ix->ev_valid = false;
+        CU(cudaEventRecord(ix->ev[0], st));
+    }
+    if ((rc = launch_segments(ix, lp, d_queries, Q, T, st))) return rc;
+    if (timing) CU(cudaEventRecord(ix->ev[1], st));
+    SearchArgs a{};
+    a.ids = ix->d_ids;
+    a.w = ix->d_w;
+    a.queries = d_queries;
+    a.seg = ix->ws_seg.p;
+    a.partial = ix->ws_partial.p;
+    a.dense_out = nullptr;
+    a.theta0 = lp.theta0;
+    a.Q = (int)Q;
+    a.T = (int)T;
+    a.k = k;
+    a.n_docs = (int)ix->n_docs;
+    a.tile_docs = lp.tile_docs;
+    a.n_tiles = lp.n_tiles;
+    a.splits = lp.splits;
+    a.tiles_per_split = lp.tiles_per_split;
+    a.cap = lp.cap;
+    if ((rc = launch_score<false>(ix, lp, a, Q, st))) return rc;
+    if (timing) CU(cudaEventRecord(ix->ev[2], st));
+    MergeArgs m{};
+    m.keys = ix->ws_partial.p;
+    m.out_ids = d_out_ids;
+    m.out_scores = d_out_scores;
+    m.Q = Q;
+    m.n_lists = lp.splits;
+    m.k_in = k;
+    m.k_out = k;
+    m.P = merge_P((int64_t)lp.splits * k, k);
+    m.id_offset = ix->doc_id_base;
+    m.fill = 1;
+    if ((rc = launch_merge(m, ix->device, ix->smem_optin, st))) return rc;
+    if (timing) {
+        CU(cudaEventRecord(ix->ev[3], st));
+        ix->ev_valid = true;
+    }
+    return BM25_OK;
+}
+
+int check_search_args(const bm25_index* ix, int64_t Q, int64_t T, int k) {
+    if (!ix) return fail(BM25_ERR_INVALID, "index handle is NULL");
+    if (Q < 0 || T < 1) return fail(BM25_ERR_INVALID, "bad query shape [%lld, %lld]", (long long)Q, (long long)T);
+    if (Q * T > 0x7fffffffLL) return fail(BM25_ERR_UNSUPPORTED, "query batch too large");
+    if (k < 1) return fail(BM25_ERR_INVALID, "k must be >= 1 (got %d)", k);
+    if (k > ix->n_docs)
+        return fail(BM25_ERR_INVALID, "kth(=-%d) out of bounds (%lld)", k, (long long)ix->n_docs);
+    if (k > BM25_MAX_K) return fail(BM25_ERR_UNSUPPORTED, "k=%d exceeds BM25_MAX_K=%d", k, BM25_MAX_K);
+    return BM25_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bm25_last_error(void) { return g_err.c_str(); }
+const char* bm25_version(void) { return "bm25_b200 0.1.0 (sm_100a)"; }
+int64_t bm25_kernel_launches(void) { return g_launches.load(); }
+
+int bm25_index_create(const int32_t* h_indptr, const int32_t* h_indices, const float* h_data, int64_t n_terms,
+                      int64_t n_docs, int64_t nnz, int device, int64_t doc_id_base, bm25_index** out) {
+    if (!out) return fail(BM25_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!h_indptr || (nnz > 0 && (!h_indices || !h_data))) return fail(BM25_ERR_INVALID, "NULL index array");
+    if (n_terms < 0 || n_docs < 0 || nnz < 0 || nnz > 0x7fffffffLL || n_docs > 0x7fffffffLL)
+        return fail(BM25_ERR_INVALID, "bad index shape (terms=%lld docs=%lld nnz=%lld)", (long long)n_terms,
+                    (long long)n_docs, (long long)nnz);
+    if (n_docs + doc_id_base > 0x7fffffffLL)
+        return fail(BM25_ERR_INVALID, "doc_id_base + n_docs exceeds int32");
+    cudaDeviceProp prop;
+    int rc = check_device(device, &prop);
+    if (rc) return rc;
+    std::vector<int32_t> c_ptr, c_idx;
+    std::vector<float> c_dat;
+    bool sorted = true, positive = true;
+    rc = canonicalise_host(h_indptr, h_indices, h_data, n_terms, n_docs, nnz, c_ptr, c_idx, c_dat, &sorted,
+                           &positive);
+    if (rc) return rc;
+    if (!sorted) {
+        h_indptr = c_ptr.data();
+        h_indices = c_idx.data();
+        h_data = c_dat.data();
+        nnz = (int64_t)c_idx.size();
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return fail(BM25_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    bm25_index* ix = new (std::nothrow) bm25_index();
+    if (!ix) return fail(BM25_ERR_OOM, "out of host memory");
+    ix->device = device;
+    ix->n_terms = n_terms;
+    ix->n_docs = n_docs;
+    ix->nnz = nnz;
+    ix->doc_id_base = doc_id_base;
+    ix->all_positive = positive;
+    ix->was_sorted = sorted;
+    ix->h_indptr.assign(h_indptr, h_indptr + n_terms + 1);
+    auto cleanup = [&](int code) {
+        bm25_index_destroy(ix);
+        return code;
+    };
+    // +64 elements of slack so that vectorised kernels may over-read past the last posting
+    if (cudaMalloc(&ix->d_indptr, (n_terms + 1 + 64) * 4) != cudaSuccess ||
+        cudaMalloc(&ix->d_ids, (nnz + 64) * 4) != cudaSuccess ||
+        cudaMalloc(&ix->d_w, (nnz + 64) * 4) != cudaSuccess) {
+        cudaGetLastError();
+        return cleanup(fail(BM25_ERR_OOM, "cudaMalloc of the index (%lld postings) failed", (long long)nnz));
+    }
+    if (cudaMemset(ix->d_ids + nnz, 0x7f, 64 * 4) != cudaSuccess || cudaMemset(ix->d_w + nnz, 0, 64 * 4) != cudaSuccess ||
+        cudaMemcpy(ix->d_indptr, h_indptr, (n_terms + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        (nnz > 0 && (cudaMemcpy(ix->d_ids, h_indices, nnz * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+                     cudaMemcpy(ix->d_w, h_data, nnz * 4, cudaMemcpyHostToDevice) != cudaSuccess))) {
+        cudaError_t e = cudaGetLastError();
+        return cleanup(fail(BM25_ERR_CUDA, "copying the index to device %d failed: %s", device,
+                            cudaGetErrorString(e)));
+    }
+    if ((rc = finish_create(ix, prop))) return cleanup(rc);
+    *out = ix;
+    return BM25_OK;
+}
+
+int bm25_index_create_device(const int32_t* d_indptr, const int32_t* d_indices, const float* d_data,
+                             int64_t n_terms, int64_t n_docs, int64_t nnz, int device, int64_t doc_id_base,
+                             int borrow, bm25_index** out) {
+    if (!out) return fail(BM25_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!d_indptr || (nnz > 0 && (!d_indices || !d_data))) return fail(BM25_ERR_INVALID, "NULL index array");
+    if (n_terms < 0 || n_docs < 0 || nnz < 0 || nnz > 0x7fffffffLL || n_docs > 0x7fffffffLL)
+        return fail(BM25_ERR_INVALID, "bad index shape (terms=%lld docs=%lld nnz=%lld)", (long long)n_terms,
+                    (long long)n_docs, (long long)nnz);
+    if (n_docs + doc_id_base > 0x7fffffffLL)
+        return fail(BM25_ERR_INVALID, "doc_id_base + n_docs exceeds int32");
+    cudaDeviceProp prop;
+    int rc = check_device(device, &prop);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(BM25_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    // validate on the device
+    unsigned long long* d_flags = nullptr;
+    unsigned long long h_flags[8] = {0};
+    CU(cudaMalloc(&d_flags, sizeof h_flags));
+    cudaMemset(d_flags, 0, sizeof h_flags);
+    if (nnz > 0) {
+        k_validate_postings<<<prop.multiProcessorCount * 8, 256>>>(d_indices, d_data, nnz, n_docs, d_flags);
+        ++g_launches;
+    }
+    if (n_terms > 0) {
+        k_validate_indptr<<<prop.multiProcessorCount * 4, 256>>>(d_indptr, d_indices, n_terms, nnz, d_flags);
+        ++g_launches;
+    }
+    cudaError_t e = cudaMemcpy(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost);
+    cudaFree(d_flags);
+    if (e != cudaSuccess) return fail(BM25_ERR_CUDA, "index validation failed: %s", cudaGetErrorString(e));
+    if (h_flags[5]) return fail(BM25_ERR_INVALID, "indptr is malformed (%llu defects)", h_flags[5]);
+    if (h_flags[0]) return fail(BM25_ERR_INVALID, "%llu doc ids are outside [0, %lld)", h_flags[0], (long long)n_docs);
+    if (h_flags[1]) return fail(BM25_ERR_INVALID, "%llu weights are not finite", h_flags[1]);
+    if (h_flags[3] != h_flags[4])
+        return fail(BM25_ERR_INVALID,
+                    "device-resident columns must be strictly increasing in doc id (%llu inversions); "
+                    "use bm25_index_create for non-canonical input",
+                    h_flags[3] - h_flags[4]);
+    bm25_index* ix = new (std::nothrow) bm25_index();
+    if (!ix) return fail(BM25_ERR_OOM, "out of host memory");
+    ix->device = device;
+    ix->n_terms = n_terms;
+    ix->n_docs = n_docs;
+    ix->nnz = nnz;
+    ix->doc_id_base = doc_id_base;
+    ix->all_positive = (h_flags[2] == 0);
+    ix->was_sorted = true;
+    ix->h_indptr.resize(n_terms + 1);
+    auto cleanup = [&](int code) {
+        bm25_index_destroy(ix);
+        return code;
+    };
+    if (cudaMemcpy(ix->h_indptr.data(), d_indptr, (n_terms + 1) * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return cleanup(fail(BM25_ERR_CUDA, "reading indptr back failed"));
+    if (borrow) {
+        ix->borrowed = true;
+        ix->d_indptr = const_cast<int32_t*>(d_indptr);
+        ix->d_ids = const_cast<int32_t*>(d_indices);
+        ix->d_w = const_cast<float*>(d_data);
+    } else {
+        if (cudaMalloc(&ix->d_indptr, (n_terms + 1 + 64) * 4) != cudaSuccess ||
+            cudaMalloc(&ix->d_ids, (nnz + 64) * 4) != cudaSuccess ||
+            cudaMalloc(&ix->d_w, (nnz + 64) * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return cleanup(fail(BM25_ERR_OOM, "cudaMalloc of the index (%lld postings) failed", (long long)nnz));
+        }
+        if (cudaMemset(ix->d_ids + nnz, 0x7f, 64 * 4) != cudaSuccess ||
+            cudaMemset(ix->d_w + nnz, 0, 64 * 4) != cudaSuccess ||
+            cudaMemcpy(ix->d_indptr, d_indptr, (n_terms + 1) * 4, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+            (nnz > 0 && (cudaMemcpy(ix->d_ids, d_indices, nnz * 4, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+                         cudaMemcpy(ix->d_w, d_data, nnz * 4, cudaMemcpyDeviceToDevice) != cudaSuccess)))
+            return cleanup(fail(BM25_ERR_CUDA, "device copy of the index failed: %s",
+                                cudaGetErrorString(cudaGetLastError())));
+    }
+    if ((rc = finish_create(ix, prop))) return cleanup(rc);
+    *out = ix;
+    return BM25_OK;
+}
+
+int bm25_index_destroy(bm25_index* ix) {
+    if (!ix) return BM25_OK;
+    {
+        DeviceGuard g(ix->device);
+        if (!ix->borrowed) {
+            if (ix->d_indptr) cudaFree(ix->d_indptr);
+            if (ix->d_ids) cudaFree(ix->d_ids);
+            if (ix->d_w) cudaFree(ix->d_w);
+        }
+        ix->ws_seg.release();
+        ix->ws_partial.release();
+        ix->ws_queries.release();
+        ix->ws_out_ids.release();
+        ix->ws_out_scores.release();
+        ix->pin_queries.release();
+        ix->pin_out_ids.release();
+        ix->pin_out_scores.release();
+        if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
+        for (auto& e : ix->ev)
+            if (e) cudaEventDestroy(e);
+    }
+    delete ix;
+    return BM25_OK;
+}
+
+int bm25_index_get_info(const bm25_index* ix, bm25_index_info* out) {
+    if (!ix || !out) return fail(BM25_ERR_INVALID, "NULL argument");
+    out->n_terms = ix->n_terms;
+    out->n_docs = ix->n_docs;
+    out->nnz = ix->nnz;
+    out->doc_id_base = ix->doc_id_base;
+    out->device_bytes = ix->device_bytes();
+    out->device = ix->device;
+    out->tile_docs = ix->tile_docs();
+    out->n_tiles = ix->n_tiles();
+    out->all_positive = ix->all_positive ? 1 : 0;
+    out->was_sorted = ix->was_sorted ? 1 : 0;
+    out->sm_count = ix->sm_count;
+    return BM25_OK;
+}
+
+int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
+    if (!ix || !name) return fail(BM25_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (!strcmp(name, "tile_docs")) {
+        if (value < 0 || value > (1 << 16)) return fail(BM25_ERR_INVALID, "tile_docs out of range");
+        ix->opt_tile_docs = (int)value;
+    } else if (!strcmp(name, "splits")) {
+        if (value < 0 || value > 65536) return fail(BM25_ERR_INVALID, "splits out of range");
+        ix->opt_splits = (int)value;
+    } else if (!strcmp(name, "force_general")) {
+        ix->opt_force_general = value ? 1 : 0;
+    } else if (!strcmp(name, "timing")) {
+        ix->opt_timing = value ? 1 : 0;
+    } else {
+        return fail(BM25_ERR_INVALID, "unknown option '%s'", name);
+    }
+    return BM25_OK;
+}
+
+int bm25_index_get_timing(bm25_index* ix, float* out_ms3) {
+    if (!ix || !out_ms3) return fail(BM25_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (!ix->ev_valid) return fail(BM25_ERR_INVALID, "no timed search recorded (set option \"timing\" to 1 first)");
+    DeviceGuard g(ix->device);
+    CU(cudaEventSynchronize(ix->ev[3]));
+    for (int i = 0; i < 3; ++i) CU(cudaEventElapsedTime(out_ms3 + i, ix->ev[i], ix->ev[i + 1]));
+    return BM25_OK;
+}
+
+int bm25_search(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T, int k, int32_t* d_out_ids,
+                float* d_out_scores, void* cuda_stream) {
+    int rc = check_search_args(ix, Q, T, k);
+    if (rc) return rc;
+    if (Q == 0) return BM25_OK;
+    if (!d_queries || !d_out_ids || !d_out_scores) return fail(BM25_ERR_INVALID, "NULL buffer");
+    DeviceGuard g(ix->device);
+    if (!g.ok) return fail(BM25_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    return search_locked(ix, d_queries, Q, T, k, d_out_ids, d_out_scores, (cudaStream_t)cuda_stream);
+}
+
+int bm25_search_host(bm25_index* ix, const int32_t* h_queries, int64_t Q, int64_t T, int k, int32_t* h_out_ids,
+                     float* h_out_scores) {
+    int rc = check_search_args(ix, Q, T, k);
+    if (rc) return rc;
+    if (Q == 0) return BM25_OK;
+    if (!h_queries || !h_out_ids || !h_out_scores) return fail(BM25_ERR_INVALID, "NULL buffer");
+    for (int64_t i = 0; i < Q * T; ++i)
+        if (h_queries[i] >= ix->n_terms)
+            return fail(BM25_ERR_INVALID,
+                        "The maximum token ID in the query (%d) is higher than the number of tokens in the index.",
+                        h_queries[i]);
+    DeviceGuard g(ix->device);
+    if (!g.ok) return fail(BM25_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    const size_t nq = (size_t)Q * T, no = (size_t)Q * k;
+    if ((rc = ix->pin_queries.reserve(nq)) || (rc = ix->pin_out_ids.reserve(no)) ||
+        (rc = ix->pin_out_scores.reserve(no)) || (rc = ix->ws_queries.reserve(nq)) ||
+        (rc = ix->ws_out_ids.reserve(no)) || (rc = ix->ws_out_scores.reserve(no)))
+        return rc;
+    cudaStream_t st = ix->own_stream;
+    memcpy(ix->pin_queries.p, h_queries, nq * 4);
+    CU(cudaMemcpyAsync(ix->ws_queries.p, ix->pin_queries.p, nq * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = search_locked(ix, ix->ws_queries.p, Q, T, k, ix->ws_out_ids.p, ix->ws_out_scores.p, st))) return rc;
+    CU(cudaMemcpyAsync(ix->pin_out_ids.p, ix->ws_out_ids.p, no * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ix->pin_out_scores.p, ix->ws_out_scores.p, no * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    memcpy(h_out_ids, ix->pin_out_ids.p, no * 4);
+    memcpy(h_out_scores, ix->pin_out_scores.p, no * 4);
+    return BM25_OK;
+}
+
+int bm25_scores_dense(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T, float* d_out,
+                      void* cuda_stream) {
+    if (!ix) return fail(BM25_ERR_INVALID, "index handle is NULL");
+    if (Q < 0 || T < 1) return fail(BM25_ERR_INVALID, "bad query shape");
+    if (Q == 0 || ix->n_docs == 0) return BM25_OK;
+    if (!d_queries || !d_out) return fail(BM25_ERR_INVALID, "NULL buffer");
+    DeviceGuard g(ix->device);
+    if (!g.ok) return fail(BM25_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    LaunchPlan lp;
+    int rc = make_plan(ix, Q, T, 1, true, &lp);
+    if (rc) return rc;
+    if ((rc = launch_segments(ix, lp, d_queries, Q, T, st))) return rc;
+    SearchArgs a{};
+    a.ids = ix->d_ids;
+    a.w = ix->d_w;
+    a.queries = d_queries;
+    a.seg = ix->ws_seg.p;
+    a.dense_out = d_out;
+    a.Q = (int)Q;
+    a.T = (int)T;
+    a.k = 1;
+    a.n_docs = (int)ix->n_docs;
+    a.tile_docs = lp.tile_docs;
+    a.n_tiles = lp.n_tiles;
+    a.splits = lp.splits;
+    a.tiles_per_split = lp.tiles_per_split;
+    a.cap = 0;
+    return launch_score<true>(ix, lp, a, Q, st);
+}
+
+int bm25_scores_dense_host(bm25_index* ix, const int32_t* h_queries, int64_t Q, int64_t T, float* h_out) {
+    if (!ix) return fail(BM25_ERR_INVALID, "index handle is NULL");
+    if (Q < 0 || T < 1) return fail(BM25_ERR_INVALID, "bad query shape");
+    if (Q == 0 || ix->n_docs == 0) return BM25_OK;
+    if (!h_queries || !h_out) return fail(BM25_ERR_INVALID, "NULL buffer");
+    for (int64_t i = 0; i < Q * T; ++i)
+        if (h_queries[i] >= ix->n_terms) return fail(BM25_ERR_INVALID, "token id %d out of range", h_queries[i]);
+    DeviceGuard g(ix->device);
+    if (!g.ok) return fail(BM25_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
+    int32_t* d_q = nullptr;
+    float* d_o = nullptr;
+    CU(cudaMalloc(&d_q, Q * T * 4));
+    if (cudaMalloc(&d_o, (size_t)Q * ix->n_docs * 4) != cudaSuccess) {
+        cudaFree(d_q);
+        cudaGetLastError();
+        return fail(BM25_ERR_OOM, "cudaMalloc of the dense score slab failed");
+    }
+    int rc = BM25_OK;
+    if (cudaMemcpy(d_q, h_queries, Q * T * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+        rc = fail(BM25_ERR_CUDA, "H2D of queries failed");
+    if (!rc) rc = bm25_scores_dense(ix, d_q, Q, T, d_o, ix->own_stream);
+    if (!rc && cudaStreamSynchronize(ix->own_stream) != cudaSuccess)
+        rc = fail(BM25_ERR_CUDA, "dense scoring failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!rc && cudaMemcpy(h_out, d_o, (size_t)Q * ix->n_docs * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail(BM25_ERR_CUDA, "D2H of dense scores failed");
+    cudaFree(d_q);
+    cudaFree(d_o);
+    return rc;
+}
+
+int bm25_merge_topk(const int32_t* d_ids, const float* d_scores, int n_lists, int64_t Q, int k_in, int k_out,
+                    int32_t* d_out_ids, float* d_out_scores, int device, void* cuda_stream) {
+    if (n_lists < 1 || k_in < 1 || k_out < 1 || Q < 0) return fail(BM25_ERR_INVALID, "bad merge shape");
+    if ((int64_t)n_lists * k_in < k_out)
+        return fail(BM25_ERR_INVALID, "merge needs n_lists*k_in >= k_out (%d*%d < %d)", n_lists, k_in, k_out);
+    if (k_out > BM25_MAX_K) return fail(BM25_ERR_UNSUPPORTED, "k_out=%d exceeds BM25_MAX_K", k_out);
+    if (Q == 0) return BM25_OK;
+    if (!d_ids || !d_scores || !d_out_ids || !d_out_scores) return fail(BM25_ERR_INVALID, "NULL buffer");
+    cudaDeviceProp prop;
+    int rc = check_device(device, &prop);
+    if (rc) return rc;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(BM25_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    MergeArgs m{};
+    m.keys = nullptr;
+    m.in_ids = d_ids;
+    m.in_scores = d_scores;
+    m.out_ids = d_out_ids;
+    m.out_scores = d_out_scores;
+    m.Q = Q;
+    m.n_lists = n_lists;
+    m.k_in = k_in;
+    m.k_out = k_out;
+    m.P = merge_P((int64_t)n_lists * k_in, k_out);
+    m.id_offset = 0;
+    m.fill = 0;
+    return launch_merge(m, device, prop.sharedMemPerBlockOptin, (cudaStream_t)cuda_stream);
+}
+
+int bm25_posting_bytes(const bm25_index* ix, const int32_t* h_queries, int64_t Q, int64_t T, int k,
+                       int64_t* out_bytes) {
+    if (!ix || !h_queries || !out_bytes) return fail(BM25_ERR_INVALID, "NULL argument");
+    int64_t postings = 0;
+    for (int64_t i = 0; i < Q * T; ++i) {
+        const int32_t t = h_queries[i];
+        if (t < 0) continue;
+        if (t >= ix->n_terms) return fail(BM25_ERR_INVALID, "token id %d out of range", t);
+        postings += ix->h_indptr[t + 1] - ix->h_indptr[t];
+    }
+    *out_bytes = 8 * postings + 8 * (int64_t)k * Q;
+    return BM25_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+"""DeviceIndex: thin Python owner of a `bm25_index*` handle (include/bm25_b200.h).
+
+Everything numerical happens inside libbm25_b200.so; this file only marshals numpy arrays / torch
+CUDA tensors into raw pointers.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+
+def _as_c(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a: np.ndarray):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+class DeviceIndex:
+    """An HBM-resident CSC BM25 index (terms = columns, documents = rows).
+
+    Parameters mirror what `BM25v.index` receives (reference bm25_native.py:59-74) plus the
+    on-disk bm25s layout (indptr / indices / data, animal_index_bm25/*.csc.index.npy).
+    """
+
+    def __init__(self, indptr, indices, data, n_docs: int, device: int = 0, doc_id_base: int = 0):
+        lib = _lib.load()
+        indptr = _as_c(indptr, np.int32)
+        indices = _as_c(indices, np.int32)
+        data = _as_c(data, np.float32)
+        if indptr.ndim != 1 or indptr.shape[0] < 1:
+            raise ValueError("indptr must be a 1-D array with at least one element")
+        if indices.shape != data.shape or indices.ndim != 1:
+            raise ValueError("indices and data must be 1-D arrays of equal length")
+        self._h = ctypes.c_void_p()
+        self._keepalive = None
+        _lib.check(lib.bm25_index_create(_ptr(indptr), _ptr(indices), _ptr(data), indptr.shape[0] - 1,
+                                         int(n_docs), indices.shape[0], int(device), int(doc_id_base),
+                                         ctypes.byref(self._h)))
+        self.device = int(device)
+
+    @classmethod
+    def from_torch(cls, indptr, indices, data, n_docs: int, doc_id_base: int = 0, borrow: bool = True):
+        """Build from CUDA tensors already in HBM (int32 indptr/indices, fp32 data, canonical CSC).
+        With ``borrow`` the tensors are used in place (kept alive by this object)."""
+        import torch
+
+        lib = _lib.load()
+        if not (indptr.is_cuda and indices.is_cuda and data.is_cuda):
+            raise ValueError("from_torch expects CUDA tensors")
+        if indptr.dtype != torch.int32 or indices.dtype != torch.int32 or data.dtype != torch.float32:
+            raise ValueError("from_torch expects int32 indptr/indices and float32 data")
+        indptr, indices, data = indptr.contiguous(), indices.contiguous(), data.contiguous()
+        torch.cuda.synchronize(indices.device)
+        self = cls.__new__(cls)
+        self._h = ctypes.c_void_p()
+        self.device = indices.device.index or 0
+        self._keepalive = (indptr, indices, data) if borrow else None
+        _lib.check(lib.bm25_index_create_device(
+            ctypes.c_void_p(indptr.data_ptr()), ctypes.c_void_p(indices.data_ptr()),
+            ctypes.c_void_p(data.data_ptr()), indptr.numel() - 1, int(n_docs), indices.numel(),
+            self.device, int(doc_id_base), 1 if borrow else 0, ctypes.byref(self._h)))
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            _lib.load().bm25_index_destroy(h)
+        self._keepalive = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _handle(self):
+        if not self._h:
+            raise ValueError("index is closed")
+        return self._h
+
+    @property
+    def info(self) -> _lib.IndexInfo:
+        out = _lib.IndexInfo()
+        _lib.check(_lib.load().bm25_index_get_info(self._handle(), ctypes.byref(out)))
+        return out
+
+    @property
+    def n_docs(self) -> int:
+        return int(self.info.n_docs)
+
+    @property
+    def n_terms(self) -> int:
+        return int(self.info.n_terms)
+
+    def set_option(self, name: str, value: int):
+        _lib.check(_lib.load().bm25_index_set_option(self._handle(), name.encode(), int(value)))
+
+    def last_timing_ms(self):
+        """(segments, score+topk, merge) device ms of the last search; needs set_option("timing", 1)."""
+        out = (ctypes.c_float * 3)()
+        _lib.check(_lib.load().bm25_index_get_timing(self._handle(), out))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    # ------------------------------------------------------------------------------------------
+    def search(self, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Host-buffer search: ``queries`` int32 [Q,T] (-1 padded) -> (int32 [Q,k], fp32 [Q,k])."""
+        q = _as_c(queries, np.int32)
+        if q.ndim != 2:
+            raise ValueError("queries must be 2-D [Q, T]")
+        qn, tn = q.shape
+        ids = np.zeros((qn, int(k)), np.int32)
+        scores = np.zeros((qn, int(k)), np.float32)
+        if tn == 0:
+            q = np.full((qn, 1), -1, np.int32)
+            tn = 1
+        _lib.check(_lib.load().bm25_search_host(self._handle(), _ptr(q), qn, tn, int(k), _ptr(ids), _ptr(scores)))
+        return ids, scores
+
+    def search_device(self, queries, k: int, out_ids=None, out_scores=None, stream: Optional[int] = None):
+        """Stream-ordered search on torch CUDA tensors (queries int32 [Q,T]); returns
+        (ids int32 [Q,k], scores fp32 [Q,k]) CUDA tensors.  Asynchronous."""
+        import torch
+
+        if not queries.is_cuda or queries.dtype != torch.int32 or queries.dim() != 2:
+            raise ValueError("queries must be a 2-D int32 CUDA tensor")
+        queries = queries.contiguous()
+        qn, tn = queries.shape
+        if out_ids is None:
+            out_ids = torch.empty((qn, k), dtype=torch.int32, device=queries.device)
+        if out_scores is None:
+            out_scores = torch.empty((qn, k), dtype=torch.float32, device=queries.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(queries.device).cuda_stream
+        _lib.check(_lib.load().bm25_search(self._handle(), ctypes.c_void_p(queries.data_ptr()), qn, tn, int(k),
+                                           ctypes.c_void_p(out_ids.data_ptr()),
+                                           ctypes.c_void_p(out_scores.data_ptr()), ctypes.c_void_p(stream)))
+        return out_ids, out_scores
+
+    def scores_dense(self, queries: np.ndarray) -> np.ndarray:
+        """Dense per-query score vectors, fp32 [Q, n_docs] (parity/debug)."""
+        q = _as_c(queries, np.int32)
+        if q.ndim != 2:
+            raise ValueError("queries must be 2-D [Q, T]")
+        out = np.zeros((q.shape[0], self.n_docs), np.float32)
+        if q.shape[1] == 0 or q.shape[0] == 0:
+            return out
+        _lib.check(_lib.load().bm25_scores_dense_host(self._handle(), _ptr(q), q.shape[0], q.shape[1], _ptr(out)))
+        return out
+
+    def posting_bytes(self, queries: np.ndarray, k: int) -> int:
+        q = _as_c(queries, np.int32)
+        out = ctypes.c_int64(0)
+        _lib.check(_lib.load().bm25_posting_bytes(self._handle(), _ptr(q), q.shape[0], q.shape[1], int(k),
+                                                  ctypes.byref(out)))
+        return int(out.value)
+
+
+def merge_topk_device(ids, scores, k_out: int, stream: Optional[int] = None):
+    """Merge all-gathered shard results: ids/scores CUDA tensors [L, Q, k_in] -> ([Q,k_out], [Q,k_out])."""
+    import torch
+
+    if ids.dim() != 3 or ids.shape != scores.shape:
+        raise ValueError("ids/scores must be [n_lists, Q, k_in]")
+    ids, scores = ids.contiguous(), scores.contiguous()
+    n_lists, qn, k_in = ids.shape
+    out_ids = torch.empty((qn, k_out), dtype=torch.int32, device=ids.device)
+    out_scores = torch.empty((qn, k_out), dtype=torch.float32, device=ids.device)
+    if stream is None:
+        stream = torch.cuda.current_stream(ids.device).cuda_stream
+    _lib.check(_lib.load().bm25_merge_topk(ctypes.c_void_p(ids.data_ptr()), ctypes.c_void_p(scores.data_ptr()),
+                                           n_lists, qn, k_in, int(k_out), ctypes.c_void_p(out_ids.data_ptr()),
+                                           ctypes.c_void_p(out_scores.data_ptr()), ids.device.index or 0,
+                                           ctypes.c_void_p(stream)))
+    return out_ids, out_scores
+
+
+def kernel_launches() -> int:
+    return int(_lib.load().bm25_kernel_launches())

@@ -1,0 +1,46 @@
+"""Developer timing probe (not the bench): per-kernel device times for named workloads."""
+import argparse
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from mojo_bm25_b200 import engine, synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workloads", default="B")
+ap.add_argument("--configs", default="0:0", help="comma list of tile_docs:splits")
+ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--scale", type=float, default=1.0)
+args = ap.parse_args()
+
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+for wl in args.workloads.split(","):
+    idx, q, k = synth.make_workload(wl, device="cuda", scale=args.scale)
+    index = engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs)
+    index.set_option("timing", 1)
+    qn = q.cpu().numpy()
+    pbytes = index.posting_bytes(qn, 0)
+    print(f"# {wl}: docs={idx.n_docs} terms={idx.n_terms} nnz={idx.nnz} Q={q.shape[0]} T={q.shape[1]} k={k} "
+          f"posting_bytes={pbytes/1e9:.3f} GB", flush=True)
+    for cfg in args.configs.split(","):
+        tile, splits = (int(x) for x in cfg.split(":"))
+        index.set_option("tile_docs", tile)
+        index.set_option("splits", splits)
+        times = []
+        for it in range(args.iters + 2):
+            flush.zero_()
+            index.search_device(q, k)
+            times.append(index.last_timing_ms())
+        t = np.array(times[2:])
+        seg, score, merge = np.median(t, axis=0)
+        tot = seg + score + merge
+        print(json.dumps(dict(workload=wl, tile_docs=index.info.tile_docs, splits=splits, seg_ms=round(float(seg), 4),
+                              score_ms=round(float(score), 4), merge_ms=round(float(merge), 4),
+                              qps=round(q.shape[0] / tot * 1e3, 1), score_GBps=round(pbytes / score / 1e6, 1))), flush=True)
+    index.close()
+    del idx, index
+    torch.cuda.empty_cache()

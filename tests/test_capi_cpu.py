@@ -1,0 +1,70 @@
+"""CPU-side checks of the C-ABI library: it builds, loads, exports every symbol that
+include/bm25_b200.h declares, and fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from mojo_bm25_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "bm25_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bm25_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_all_declared_symbols():
+    so = build.build()
+    assert os.path.exists(so)
+    lib = ctypes.CDLL(so)
+    declared = _declared_symbols()
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/bm25_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == declared
+
+
+def test_version_and_launch_counter():
+    lib = _lib.load()
+    assert b"sm_100a" in lib.bm25_version()
+    assert lib.bm25_kernel_launches() >= 0
+
+
+def test_sass_contains_only_sm100a():
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", build.build()], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mojo_bm25_b200.engine import DeviceIndex
+
+    indptr = np.array([0, 1, 2], np.int32)
+    with pytest.raises(Exception) as ei:
+        DeviceIndex(indptr, np.array([0, 1], np.int32), np.array([1.0, 2.0], np.float32), n_docs=2)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_argument_validation_happens_before_device_use():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.bm25_index_create(None, None, None, 0, 0, 0, 0, 0, ctypes.byref(h))
+    assert rc == _lib.ERR_INVALID
+    assert b"NULL" in lib.bm25_last_error()
+    rc = lib.bm25_search(None, None, 1, 1, 1, None, None, None)
+    assert rc == _lib.ERR_INVALID
