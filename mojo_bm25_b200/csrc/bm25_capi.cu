@@ -296,8 +296,12 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
     static thread_local size_t configured[64] = {0};
     auto kern = k_score_topk<kDense>;
     if (configured[ix->device % 64] < lp.smem) {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ix->smem_optin)));
-        configured[ix->device % 64] = ix->smem_optin;
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, kern));
+        const size_t max_dyn = ix->smem_optin - fa.sharedSizeBytes;
+        if (lp.smem > max_dyn) return fail(BM25_ERR_UNSUPPORTED, "kernel needs %zu B of shared memory", lp.smem);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+        configured[ix->device % 64] = max_dyn;
     }
     const int64_t grid = Q * lp.splits;
     if (grid > 0x7fffffffLL) return fail(BM25_ERR_UNSUPPORTED, "grid too large");
@@ -324,8 +328,12 @@ int launch_merge(const MergeArgs& m, int device, size_t smem_optin, cudaStream_t
     const size_t smem = (size_t)m.P * 8 + (size_t)m.k_out + 16;
     static thread_local size_t configured[64] = {0};
     if (smem > 48 * 1024 && configured[device % 64] < smem) {
-        CU(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin));
-        configured[device % 64] = smem_optin;
+        cudaFuncAttributes fa;
+        CU(cudaFuncGetAttributes(&fa, k_merge));
+        const size_t max_dyn = smem_optin - fa.sharedSizeBytes;
+        if (smem > max_dyn) return fail(BM25_ERR_UNSUPPORTED, "merge needs %zu B of shared memory", smem);
+        CU(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+        configured[device % 64] = max_dyn;
     }
     k_merge<<<(unsigned)m.Q, kThreads, smem, st>>>(m);
     ++g_launches;
