@@ -105,10 +105,12 @@ int bm25_scores_dense_host(bm25_index* index, const int32_t* h_queries, int64_t 
 
 /* Multi-GPU final merge (new; the reference is single-device): merges n_lists candidate lists
  * laid out [n_lists, Q, k_in] (the layout an all-gather of per-shard results produces) into the
- * global top k_out per query.  Device pointers on `device`. */
-int bm25_merge_topk(const int32_t* d_ids, const float* d_scores, int n_lists, int64_t Q, int k_in,
-                    int k_out, int32_t* d_out_ids, float* d_out_scores, int device,
-                    void* cuda_stream);
+ * global top k_out per query.  `list_stride` = elements between consecutive lists in both arrays
+ * (0 = Q*k_in, i.e. dense), so ids and scores may live interleaved in one all-gather buffer
+ * [n_lists][2][Q][k_in].  Device pointers on `device`. */
+int bm25_merge_topk(const int32_t* d_ids, const float* d_scores, int n_lists, int64_t list_stride,
+                    int64_t Q, int k_in, int k_out, int32_t* d_out_ids, float* d_out_scores,
+                    int device, void* cuda_stream);
 
 /* Algorithmic bytes of a batch: sum_q 8*sum_t df(t) + 8*k.  Host queries. */
 int bm25_posting_bytes(const bm25_index* index, const int32_t* h_queries, int64_t Q, int64_t T,

@@ -61,7 +61,7 @@ def load(rebuild_if_stale: bool = True):
     lib.bm25_search_host.argtypes = [vp, vp, i64, i64, i32, vp, vp]
     lib.bm25_scores_dense.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.bm25_scores_dense_host.argtypes = [vp, vp, i64, i64, vp]
-    lib.bm25_merge_topk.argtypes = [vp, vp, i32, i64, i32, i32, vp, vp, i32, vp]
+    lib.bm25_merge_topk.argtypes = [vp, vp, i32, i64, i64, i32, i32, vp, vp, i32, vp]
     lib.bm25_posting_bytes.argtypes = [vp, vp, i64, i64, i32, ctypes.POINTER(i64)]
     lib.bm25_kernel_launches.argtypes = []
     lib.bm25_kernel_launches.restype = i64

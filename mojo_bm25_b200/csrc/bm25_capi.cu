@@ -735,8 +735,10 @@ int bm25_scores_dense_host(bm25_index* ix, const int32_t* h_queries, int64_t Q, 
     return rc;
 }
 
-int bm25_merge_topk(const int32_t* d_ids, const float* d_scores, int n_lists, int64_t Q, int k_in, int k_out,
-                    int32_t* d_out_ids, float* d_out_scores, int device, void* cuda_stream) {
+int bm25_merge_topk(const int32_t* d_ids, const float* d_scores, int n_lists, int64_t list_stride, int64_t Q,
+                    int k_in, int k_out, int32_t* d_out_ids, float* d_out_scores, int device, void* cuda_stream) {
+    if (list_stride == 0) list_stride = Q * k_in;
+    if (list_stride < Q * k_in) return fail(BM25_ERR_INVALID, "list_stride smaller than one list");
     if (n_lists < 1 || k_in < 1 || k_out < 1 || Q < 0) return fail(BM25_ERR_INVALID, "bad merge shape");
     if ((int64_t)n_lists * k_in < k_out)
         return fail(BM25_ERR_INVALID, "merge needs n_lists*k_in >= k_out (%d*%d < %d)", n_lists, k_in, k_out);
@@ -755,6 +757,7 @@ int bm25_merge_topk(const int32_t* d_ids, const float* d_scores, int n_lists, in
     m.out_ids = d_out_ids;
     m.out_scores = d_out_scores;
     m.Q = Q;
+    m.list_stride = list_stride;
     m.n_lists = n_lists;
     m.k_in = k_in;
     m.k_out = k_out;

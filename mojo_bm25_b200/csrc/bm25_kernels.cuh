@@ -260,6 +260,7 @@ struct MergeArgs {
     int32_t* __restrict__ out_ids;
     float* __restrict__ out_scores;
     int64_t Q;
+    int64_t list_stride; // elements between consecutive lists of in_ids / in_scores
     int n_lists, k_in, k_out, P;
     int64_t id_offset;   // added to key doc ids on output (doc_id_base); 0 for shard merges
     int fill;            // 1: pad with zero-score docs 0,1,2.. not already present
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
                     key = a.keys[q * total + e];
                 } else {
                     const int l = e / a.k_in, r = e - l * a.k_in;
-                    const int64_t off = ((int64_t)l * a.Q + q) * a.k_in + r;
+                    const int64_t off = (int64_t)l * a.list_stride + q * a.k_in + r;
                     key = make_key(a.in_scores[off], (uint32_t)a.in_ids[off]);
                 }
             }

@@ -162,20 +162,29 @@ class DeviceIndex:
         return int(out.value)
 
 
-def merge_topk_device(ids, scores, k_out: int, stream: Optional[int] = None):
-    """Merge all-gathered shard results: ids/scores CUDA tensors [L, Q, k_in] -> ([Q,k_out], [Q,k_out])."""
+def merge_topk_device(ids, scores, k_out: int, stream: Optional[int] = None, list_stride: int = 0,
+                      n_lists: Optional[int] = None, n_queries: Optional[int] = None, k_in: Optional[int] = None):
+    """Merge all-gathered shard results into the global top-k (bm25_merge_topk).
+
+    Dense form: ids/scores CUDA tensors [L, Q, k_in].  Packed form (one all-gather buffer
+    [L][2][Q][k_in]): pass the id and score views of list 0 plus ``list_stride`` (elements),
+    ``n_lists``, ``n_queries`` and ``k_in`` explicitly."""
     import torch
 
-    if ids.dim() != 3 or ids.shape != scores.shape:
-        raise ValueError("ids/scores must be [n_lists, Q, k_in]")
-    ids, scores = ids.contiguous(), scores.contiguous()
-    n_lists, qn, k_in = ids.shape
-    out_ids = torch.empty((qn, k_out), dtype=torch.int32, device=ids.device)
-    out_scores = torch.empty((qn, k_out), dtype=torch.float32, device=ids.device)
+    if list_stride == 0:
+        if ids.dim() != 3 or ids.shape != scores.shape:
+            raise ValueError("ids/scores must be [n_lists, Q, k_in]")
+        ids, scores = ids.contiguous(), scores.contiguous()
+        n_lists, n_queries, k_in = ids.shape
+    if ids.dtype != torch.int32 or scores.dtype != torch.float32:
+        raise ValueError("ids must be int32 and scores float32")
+    out_ids = torch.empty((n_queries, k_out), dtype=torch.int32, device=ids.device)
+    out_scores = torch.empty((n_queries, k_out), dtype=torch.float32, device=ids.device)
     if stream is None:
         stream = torch.cuda.current_stream(ids.device).cuda_stream
     _lib.check(_lib.load().bm25_merge_topk(ctypes.c_void_p(ids.data_ptr()), ctypes.c_void_p(scores.data_ptr()),
-                                           n_lists, qn, k_in, int(k_out), ctypes.c_void_p(out_ids.data_ptr()),
+                                           int(n_lists), int(list_stride), int(n_queries), int(k_in), int(k_out),
+                                           ctypes.c_void_p(out_ids.data_ptr()),
                                            ctypes.c_void_p(out_scores.data_ptr()), ids.device.index or 0,
                                            ctypes.c_void_p(stream)))
     return out_ids, out_scores

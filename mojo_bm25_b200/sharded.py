@@ -1,0 +1,107 @@
+"""Multi-GPU query path (new design; the reference is single-device).
+
+One process per GPU (torch.distributed, NCCL over NVLink 5 / NVSwitch).
+
+* ``DocShardedSearcher``: the index is partitioned by document range, rank g owning documents
+  [base_g, base_g + n_g).  Every rank scores the SAME query batch against its shard, writes its
+  local top-k straight into the send half of one packed all-gather buffer ([2][Q][k]: ids, then
+  score bits), one ``all_gather_into_tensor`` moves Q*k*8 B per rank, and bm25_merge_topk selects
+  the global top-k from the [W][2][Q][k] buffer on every rank.  Scores are comparable across
+  shards because the weights are precomputed with global statistics at index time.
+* ``QuerySplitSearcher``: the (small) index is replicated and the query batch is split across
+  ranks -- no data-path collective except the optional gather of results.
+
+The local-search and merge callables are injectable so that the host logic (partitioning,
+packing, the collective) is exercised on CPU with the gloo backend in tests/.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def doc_range_of_rank(n_docs: int, world: int, rank: int) -> Tuple[int, int]:
+    """[lo, hi) of the documents rank owns: contiguous ranges of ceil(N / world)."""
+    per = -(-int(n_docs) // int(world))
+    lo = min(int(n_docs), rank * per)
+    return lo, min(int(n_docs), lo + per)
+
+
+class DocShardedSearcher:
+    def __init__(self, local_search: Callable, k: int, merge: Optional[Callable] = None,
+                 group: Optional[dist.ProcessGroup] = None):
+        """``local_search(queries, k, out_ids, out_scores)`` fills the two [Q,k] outputs with the
+        shard-local top-k (GLOBAL doc ids).  ``merge(ids_view, scores_view, k, list_stride,
+        n_lists, n_queries, k_in)`` defaults to the CUDA merge kernel."""
+        self.local_search = local_search
+        self.k = int(k)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if merge is None:
+            from .engine import merge_topk_device
+
+            merge = merge_topk_device
+        self.merge = merge
+        self._send = None
+        self._recv = None
+
+    @classmethod
+    def from_index(cls, index, k: int, group=None):
+        return cls(lambda q, kk, oi, os_: index.search_device(q, kk, out_ids=oi, out_scores=os_), k, group=group)
+
+    def _buffers(self, n_queries: int, device):
+        shape = (2, n_queries, self.k)
+        if self._send is None or self._send.shape != shape or self._send.device != device:
+            self._send = torch.empty(shape, dtype=torch.int32, device=device)
+            self._recv = torch.empty((self.world,) + shape, dtype=torch.int32, device=device)
+        return self._send, self._recv
+
+    def search(self, queries: torch.Tensor):
+        """queries int32 [Q,T] (identical on all ranks) -> global (ids [Q,k], scores [Q,k])."""
+        n_queries = queries.shape[0]
+        send, recv = self._buffers(n_queries, queries.device)
+        self.local_search(queries, self.k, send[0], send[1].view(torch.float32))
+        if self.world > 1:
+            dist.all_gather_into_tensor(recv.view(self.world * 2, n_queries, self.k), send, group=self.group)
+        else:
+            recv[0].copy_(send)
+        return self.merge(recv[0, 0], recv[0, 1].view(torch.float32), self.k,
+                          list_stride=2 * n_queries * self.k, n_lists=self.world,
+                          n_queries=n_queries, k_in=self.k)
+
+
+class QuerySplitSearcher:
+    def __init__(self, local_search: Callable, k: int, group: Optional[dist.ProcessGroup] = None):
+        self.local_search = local_search
+        self.k = int(k)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    @classmethod
+    def from_index(cls, index, k: int, group=None):
+        return cls(lambda q, kk, oi, os_: index.search_device(q, kk, out_ids=oi, out_scores=os_), k, group=group)
+
+    def my_slice(self, n_queries: int) -> Tuple[int, int]:
+        per = -(-n_queries // self.world)
+        lo = min(n_queries, self.rank * per)
+        return lo, min(n_queries, lo + per)
+
+    def search(self, queries: torch.Tensor, gather: bool = True):
+        """queries int32 [Q,T] (identical on all ranks).  Each rank scores its contiguous slice;
+        with ``gather`` every rank receives the full [Q,k] result."""
+        n_queries = queries.shape[0]
+        per = -(-n_queries // self.world)
+        lo, hi = self.my_slice(n_queries)
+        out = torch.zeros((2, per, self.k), dtype=torch.int32, device=queries.device)
+        if hi > lo:
+            self.local_search(queries[lo:hi].contiguous(), self.k, out[0, : hi - lo], out[1, : hi - lo].view(torch.float32))
+        if not gather or self.world == 1:
+            return out[0, : hi - lo], out[1, : hi - lo].view(torch.float32)
+        recv = torch.empty((self.world, 2, per, self.k), dtype=torch.int32, device=queries.device)
+        dist.all_gather_into_tensor(recv.view(self.world * 2, per, self.k), out, group=self.group)
+        ids = recv[:, 0].reshape(self.world * per, self.k)[:n_queries]
+        scores = recv[:, 1].reshape(self.world * per, self.k)[:n_queries].view(torch.float32)
+        return ids, scores

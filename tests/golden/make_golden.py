@@ -10,6 +10,7 @@ feeds them fixed inputs and stores inputs + outputs:
   * golden_bundled.json  -- G1: bundled animal_index_bm25 CSC arrays, queries, BM25v outputs
   * golden_dense.json    -- G2/G3: fox + animal corpora through bm25.BM25 (scores, top-n order)
   * golden_selfcheck.json-- G4: bm25_native.py __main__ self check
+  * animal_index_bm25/   -- the bundled bm25s on-disk index itself (7 data files, 1.4 KB)
   * golden_random.npz    -- R*: seeded random CSC matrices through BM25v.search plus the
                             reference's dense per-query score vectors (bitwise fp32)
 
@@ -203,7 +204,21 @@ def golden_random():
     np.savez_compressed(os.path.join(HERE, "golden_random.npz"), **store)
 
 
+def golden_disk_index():
+    """Byte-for-byte copy of the bundled on-disk index (data fixture for the loader/writer tests)."""
+    import shutil
+
+    dst = os.path.join(HERE, "animal_index_bm25")
+    shutil.rmtree(dst, ignore_errors=True)
+    shutil.copytree(os.path.join(REF, "animal_index_bm25"), dst)
+    for root, _, files in os.walk(dst):
+        for f in files:
+            os.chmod(os.path.join(root, f), 0o644)
+        os.chmod(root, 0o755)
+
+
 if __name__ == "__main__":
+    golden_disk_index()
     golden_bundled()
     golden_dense()
     golden_selfcheck()
