@@ -158,6 +158,7 @@ struct bm25_index {
     std::vector<int32_t> h_indptr;  // host copy for byte accounting / validation
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
+    int opt_stage = 0, opt_warps = 0, opt_cap = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace
@@ -173,9 +174,9 @@ struct bm25_index {
 
     int tile_docs() const {
         int t = opt_tile_docs > 0 ? opt_tile_docs : 16384;
-        int64_t need = ((n_docs + kChunk - 1) / kChunk) * kChunk;
-        if (need < t) t = (int)std::max<int64_t>(need, kChunk);
-        t = ((t + kChunk - 1) / kChunk) * kChunk;
+        const int64_t need = std::max<int64_t>(((n_docs + 1023) / 1024) * 1024, 1024);
+        if (need < t) t = (int)need;
+        t = ((t + 1023) / 1024) * 1024;
         return t;
     }
     int n_tiles() const { return (int)std::max<int64_t>(1, (n_docs + tile_docs() - 1) / tile_docs()); }
@@ -256,31 +257,40 @@ int canonicalise_host(const int32_t* indptr, const int32_t* indices, const float
 }
 
 struct LaunchPlan {
-    int tile_docs, n_tiles, splits, tiles_per_split, cap;
+    int tile_docs, n_tiles, splits, tiles_per_split, cap, stage, warps, general;
     size_t smem;
     u64 theta0;
 };
 
+size_t score_smem(int tile_docs, int stage, int cap, int64_t T) {
+    return (size_t)tile_docs * 4 + (size_t)stage * 16 + (size_t)cap * 8 + 64 + (size_t)T * 24 + 128;
+}
+
 int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, bool dense, LaunchPlan* lp) {
     lp->tile_docs = ix->tile_docs();
-    lp->n_tiles = ix->n_tiles();
-    lp->cap = dense ? 0 : next_pow2((int64_t)k + kChunk);
+    lp->warps = ix->opt_warps > 0 ? ix->opt_warps : 8;
+    lp->stage = ix->opt_stage > 0 ? ((ix->opt_stage + 3) / 4) * 4 : 2048;
+    lp->cap = 0;
+    if (!dense) {
+        lp->cap = ix->opt_cap > 0 ? next_pow2(ix->opt_cap) : next_pow2(std::max(2 * (int64_t)k, (int64_t)512));
+        if (lp->cap < k + 64) lp->cap = next_pow2((int64_t)k + 64);
+    }
     // shrink the tile until the CTA fits into shared memory
     for (;;) {
-        lp->smem = (size_t)lp->tile_docs * 4 + (size_t)lp->cap * 8 + (size_t)T * 8 + 16;
+        lp->smem = dense ? (size_t)lp->tile_docs * 4 + (size_t)T * 8 + 16
+                         : score_smem(lp->tile_docs, lp->stage, lp->cap, T);
         if (lp->smem <= ix->smem_optin - 1024) break;
-        if (lp->tile_docs <= kChunk)
+        if (lp->tile_docs <= 1024)
             return fail(BM25_ERR_UNSUPPORTED, "query shape (T=%lld, k=%d) does not fit in shared memory",
                         (long long)T, k);
-        lp->tile_docs -= kChunk;
-        lp->n_tiles = (int)((ix->n_docs + lp->tile_docs - 1) / lp->tile_docs);
+        lp->tile_docs -= 1024;
     }
+    lp->n_tiles = (int)std::max<int64_t>(1, (ix->n_docs + lp->tile_docs - 1) / lp->tile_docs);
     int splits = ix->opt_splits;
     if (splits <= 0) {
         const int64_t slots = (int64_t)ix->sm_count * 2 * 4;
         splits = (int)std::max<int64_t>(1, (slots + Q - 1) / std::max<int64_t>(Q, 1));
     }
-    if (dense) splits = std::min(splits, lp->n_tiles);
     splits = std::max(1, std::min(splits, lp->n_tiles));
     lp->tiles_per_split = (lp->n_tiles + splits - 1) / splits;
     lp->splits = (lp->n_tiles + lp->tiles_per_split - 1) / lp->tiles_per_split;
@@ -288,24 +298,48 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, bool dense, LaunchPla
     // positive index: only strictly positive scores compete, zero-score docs are filled in by
     // k_merge; general index: every document competes (theta0 = 0 admits all keys).
     lp->theta0 = positive ? make_key(0.0f, 0u) : 0ull;
+    lp->general = positive ? 0 : 1;
     return BM25_OK;
 }
 
-template <bool kDense>
-int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int64_t Q, cudaStream_t st) {
+template <typename Kern>
+int configure_smem(Kern kern, size_t need, size_t smem_optin, size_t* configured) {
+    if (*configured >= need) return BM25_OK;
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kern));
+    const size_t max_dyn = smem_optin - fa.sharedSizeBytes;
+    if (need > max_dyn) return fail(BM25_ERR_UNSUPPORTED, "kernel needs %zu B of shared memory", need);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
+    *configured = max_dyn;
+    return BM25_OK;
+}
+
+template <int NCW>
+int launch_score_w(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int64_t grid, cudaStream_t st) {
     static thread_local size_t configured[64] = {0};
-    auto kern = k_score_topk<kDense>;
-    if (configured[ix->device % 64] < lp.smem) {
-        cudaFuncAttributes fa;
-        CU(cudaFuncGetAttributes(&fa, kern));
-        const size_t max_dyn = ix->smem_optin - fa.sharedSizeBytes;
-        if (lp.smem > max_dyn) return fail(BM25_ERR_UNSUPPORTED, "kernel needs %zu B of shared memory", lp.smem);
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
-        configured[ix->device % 64] = max_dyn;
-    }
+    int rc = configure_smem(k_score_topk<NCW>, lp.smem, ix->smem_optin, &configured[ix->device % 64]);
+    if (rc) return rc;
+    k_score_topk<NCW><<<(unsigned)grid, (NCW + 1) * 32, lp.smem, st>>>(a);
+    return BM25_OK;
+}
+
+int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int64_t Q, bool dense, cudaStream_t st) {
     const int64_t grid = Q * lp.splits;
     if (grid > 0x7fffffffLL) return fail(BM25_ERR_UNSUPPORTED, "grid too large");
-    kern<<<(unsigned)grid, kThreads, lp.smem, st>>>(a);
+    int rc;
+    if (dense) {
+        static thread_local size_t configured[64] = {0};
+        if ((rc = configure_smem(k_scores_dense, lp.smem, ix->smem_optin, &configured[ix->device % 64]))) return rc;
+        k_scores_dense<<<(unsigned)grid, kThreads, lp.smem, st>>>(a);
+    } else {
+        switch (lp.warps) {
+            case 4: rc = launch_score_w<4>(ix, lp, a, grid, st); break;
+            case 8: rc = launch_score_w<8>(ix, lp, a, grid, st); break;
+            case 16: rc = launch_score_w<16>(ix, lp, a, grid, st); break;
+            default: return fail(BM25_ERR_INVALID, "consumer_warps must be 4, 8 or 16");
+        }
+        if (rc) return rc;
+    }
     ++g_launches;
     CU(cudaGetLastError());
     return BM25_OK;
@@ -317,7 +351,7 @@ int launch_segments(bm25_index* ix, const LaunchPlan& lp, const int32_t* d_queri
     int rc = ix->ws_seg.reserve((size_t)n_qt * (lp.n_tiles + 1));
     if (rc) return rc;
     const int64_t blocks = (n_qt * 32 + 255) / 256;
-    k_segments<<<(unsigned)blocks, 256, 0, st>>>(ix->d_indptr, ix->d_ids, d_queries, n_qt, (int)ix->n_terms,
+    k_segments<<<(unsigned)blocks, 256, 0, st>>>(ix->d_indptr, ix->d_ids, d_queries, n_qt, (int)T, (int)ix->n_terms,
                                                  lp.tile_docs, lp.n_tiles, ix->ws_seg.p);
     ++g_launches;
     CU(cudaGetLastError());
@@ -378,7 +412,9 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.splits = lp.splits;
     a.tiles_per_split = lp.tiles_per_split;
     a.cap = lp.cap;
-    if ((rc = launch_score<false>(ix, lp, a, Q, st))) return rc;
+    a.stage_postings = lp.stage;
+    a.general = lp.general;
+    if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
     MergeArgs m{};
     m.keys = ix->ws_partial.p;
@@ -610,6 +646,16 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
     } else if (!strcmp(name, "splits")) {
         if (value < 0 || value > 65536) return fail(BM25_ERR_INVALID, "splits out of range");
         ix->opt_splits = (int)value;
+    } else if (!strcmp(name, "stage_postings")) {
+        if (value < 0 || value > (1 << 15)) return fail(BM25_ERR_INVALID, "stage_postings out of range");
+        ix->opt_stage = (int)value;
+    } else if (!strcmp(name, "consumer_warps")) {
+        if (value != 0 && value != 4 && value != 8 && value != 16)
+            return fail(BM25_ERR_INVALID, "consumer_warps must be 0, 4, 8 or 16");
+        ix->opt_warps = (int)value;
+    } else if (!strcmp(name, "cap")) {
+        if (value < 0 || value > (1 << 14)) return fail(BM25_ERR_INVALID, "cap out of range");
+        ix->opt_cap = (int)value;
     } else if (!strcmp(name, "force_general")) {
         ix->opt_force_general = value ? 1 : 0;
     } else if (!strcmp(name, "timing")) {
@@ -702,7 +748,7 @@ int bm25_scores_dense(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64
     a.splits = lp.splits;
     a.tiles_per_split = lp.tiles_per_split;
     a.cap = 0;
-    return launch_score<true>(ix, lp, a, Q, st);
+    return launch_score(ix, lp, a, Q, true, st);
 }
 
 int bm25_scores_dense_host(bm25_index* ix, const int32_t* h_queries, int64_t Q, int64_t T, float* h_out) {

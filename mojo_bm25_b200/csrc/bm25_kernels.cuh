@@ -54,22 +54,25 @@ __host__ __device__ __forceinline__ uint32_t key_doc(u64 key) { return 0xfffffff
 __host__ __device__ __forceinline__ float key_score(u64 key) { return ord_to_f32((uint32_t)(key >> 32)); }
 
 // ---------------------------------------------------------------------------------------------
-// k_segments: seg[(q*T+t)*(n_tiles+1) + j] = first posting index of term queries[q,t] whose doc
-// id is >= j*tile_docs (absolute index into ids/w); entry n_tiles is the end of the slice.
-// One warp per (query, term); lanes stride over tile boundaries.
+// k_segments: seg[(q*(n_tiles+1) + j)*T + t] = first posting index of term queries[q,t] whose doc
+// id is >= j*tile_docs (absolute index into ids/w); row n_tiles is the end of the slice.
+// Tile-major so that one tile's T boundaries are contiguous.  One warp per (query, term); lanes
+// stride over tile boundaries (binary search on doc id inside the term's posting slice).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_segments(const int32_t* __restrict__ indptr,
                                                   const int32_t* __restrict__ ids,
                                                   const int32_t* __restrict__ queries, int64_t n_qt,
-                                                  int n_terms, int tile_docs, int n_tiles,
+                                                  int T, int n_terms, int tile_docs, int n_tiles,
                                                   int32_t* __restrict__ seg) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= n_qt) return;
     const int term = queries[warp];
+    const int64_t q = warp / T;
+    const int t = (int)(warp - q * T);
     int lo0 = 0, hi0 = 0;
     if (term >= 0 && term < n_terms) { lo0 = indptr[term]; hi0 = indptr[term + 1]; }
-    int32_t* out = seg + warp * (int64_t)(n_tiles + 1);
+    int32_t* out = seg + q * (int64_t)(n_tiles + 1) * T + t;
     for (int j = lane; j <= n_tiles; j += 32) {
         int res;
         if (j == 0) res = lo0;
@@ -83,167 +86,341 @@ __global__ void __launch_bounds__(256) k_segments(const int32_t* __restrict__ in
             }
             res = lo;
         }
-        out[j] = res;
+        out[(int64_t)j * T] = res;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// block-wide bitonic sort (descending) of P = 2^m keys in shared memory
+// group barriers: the whole CTA (barrier 0) or the consumer warps of k_score_topk (barrier 1)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bitonic_sort_desc(u64* buf, int P) {
+struct CtaGroup {
+    int size, rank;
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct ConsumerGroup {
+    int size, rank;
+    __device__ __forceinline__ void sync() const {
+        asm volatile("bar.sync 1, %0;" ::"r"(size) : "memory");
+    }
+};
+
+// group-wide bitonic sort (descending) of P = 2^m keys in shared memory
+template <typename G>
+__device__ __forceinline__ void bitonic_sort_desc(u64* buf, int P, const G& g) {
     for (int size = 2; size <= P; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+            for (int i = g.rank; i < (P >> 1); i += g.size) {
                 const int a = 2 * i - (i & (stride - 1));
                 const int b = a + stride;
                 const bool desc = ((a & size) == 0);
                 const u64 x = buf[a], y = buf[b];
                 if ((x < y) == desc) { buf[a] = y; buf[b] = x; }
             }
-            __syncthreads();
+            g.sync();
         }
     }
 }
 
-// Keep the k best of the n candidates in cand[0..n) (sorted, best first), raise the threshold.
-// Must be called by all threads of the CTA with no push in flight.
-__device__ __forceinline__ void compact_candidates(u64* cand, int k, u64 theta0, int* s_ncand,
-                                                   u64* s_theta) {
-    const int n = *s_ncand;
+// Keep the k best of the n = min(*s_ncand, cap) candidates (sorted, best first) and raise the
+// threshold.  Called by every thread of the group with no push in flight.
+template <typename G>
+__device__ __forceinline__ void compact_candidates(u64* cand, int cap, int k, u64 theta0, int* s_ncand,
+                                                   u64* s_theta, const G& g) {
+    const int n = min(*s_ncand, cap);
     int P = 2;
     while (P < n) P <<= 1;
-    for (int i = n + threadIdx.x; i < P; i += blockDim.x) cand[i] = 0;
-    __syncthreads();
-    bitonic_sort_desc(cand, P);
-    if (threadIdx.x == 0) {
+    for (int i = n + g.rank; i < P; i += g.size) cand[i] = 0;
+    g.sync();
+    bitonic_sort_desc(cand, P, g);
+    if (g.rank == 0) {
         *s_ncand = n < k ? n : k;
         *s_theta = (n >= k) ? cand[k - 1] : theta0;
     }
-    __syncthreads();
+    g.sync();
 }
 
 struct SearchArgs {
     const int32_t* __restrict__ ids;      // [nnz]   doc ids, columns sorted ascending
     const float* __restrict__ w;          // [nnz]   weights
     const int32_t* __restrict__ queries;  // [Q,T]
-    const int32_t* __restrict__ seg;      // [Q,T,n_tiles+1]
+    const int32_t* __restrict__ seg;      // [Q,n_tiles+1,T]
     u64* __restrict__ partial;            // [Q,splits,k] sorted keys (0 = none)
-    float* __restrict__ dense_out;        // [Q,n_docs]  (dense-output variant only)
+    float* __restrict__ dense_out;        // [Q,n_docs]  (k_scores_dense only)
     u64 theta0;                           // initial threshold: key must be > theta0 to compete
     int Q, T, k;
     int n_docs, tile_docs, n_tiles;
     int splits, tiles_per_split, cap;
+    int stage_postings;                   // capacity of one staging buffer (multiple of 4)
+    int general;                          // 1: zero-score docs compete (weights may be <= 0)
 };
 
 // ---------------------------------------------------------------------------------------------
-// k_score_topk: CTA = (query, range of document tiles).
-// shared memory: float score[tile_docs] | u64 cand[cap] | int seg_lo[T] | int seg_hi[T]
+// k_scores_dense (parity/debug): CTA = (query, range of document tiles); direct global loads,
+// shared-memory score tile, terms strictly in query order, writes the dense [Q, n_docs] slab.
+// shared memory: float score[tile_docs] | int seg_lo[T] | int seg_hi[T]
 // ---------------------------------------------------------------------------------------------
-template <bool kDenseOut>
-__global__ void __launch_bounds__(kThreads, 2) k_score_topk(const SearchArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(kThreads, 2) k_scores_dense(const SearchArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     float* sc = reinterpret_cast<float*>(smem_raw);
-    u64* cand = reinterpret_cast<u64*>(smem_raw + (size_t)a.tile_docs * sizeof(float));
-    int* s_lo = reinterpret_cast<int*>(cand + (kDenseOut ? 0 : a.cap));
+    int* s_lo = reinterpret_cast<int*>(smem_raw + (size_t)a.tile_docs * sizeof(float));
     int* s_hi = s_lo + a.T;
-    __shared__ int s_ncand;
+    const int tid = threadIdx.x;
+    const int q = blockIdx.x / a.splits;
+    const int sp = blockIdx.x - q * a.splits;
+    const int j0 = sp * a.tiles_per_split;
+    const int j1 = min(a.n_tiles, j0 + a.tiles_per_split);
+    for (int i = tid; i < a.tile_docs; i += kThreads) sc[i] = 0.f;
+    const int32_t* segq = a.seg + (int64_t)q * a.T * (a.n_tiles + 1);
+    __syncthreads();
+    for (int j = j0; j < j1; ++j) {
+        const int base = j * a.tile_docs;
+        const int nd = min(a.tile_docs, a.n_docs - base);
+        for (int t = tid; t < a.T; t += kThreads) {
+            s_lo[t] = __ldg(segq + (int64_t)j * a.T + t);
+            s_hi[t] = __ldg(segq + (int64_t)(j + 1) * a.T + t);
+        }
+        __syncthreads();
+        for (int t = 0; t < a.T; ++t) {
+            const int lo = s_lo[t], hi = s_hi[t];
+            if (lo >= hi) continue;  // uniform
+            for (int i = lo + tid; i < hi; i += kThreads) sc[__ldg(a.ids + i) - base] += __ldg(a.w + i);
+            __syncthreads();
+        }
+        float* out = a.dense_out + (int64_t)q * a.n_docs + base;
+        for (int i = tid; i < nd; i += kThreads) { out[i] = sc[i]; sc[i] = 0.f; }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA 1-D) primitives
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk async copy; completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_score_topk: the hot kernel.  CTA = (query, range of document tiles), warp-specialised:
+//   producer warp : walks the tiles, packs the query terms' posting segments of a tile into
+//                   "rounds" that fit one staging buffer and issues them as 1-D bulk async copies
+//                   (TMA) into a 2-stage shared-memory ring, completion on mbarriers;
+//   consumer warps: wait for a round, add its pieces into the shared-memory score tile strictly
+//                   in query-term order (one fp32 add per posting, a named barrier between
+//                   terms -- a term has at most one posting per document, so no atomics), and at
+//                   the end of a tile run a barrier-free fused scan+zero that pushes only the
+//                   documents beating the running k-th best key into a candidate buffer.
+// shared memory (dynamic):
+//   float score[tile_docs] | int32 st_ids[2][stg] | float st_w[2][stg] | u64 cand[cap]
+//   | u64 full[2], empty[2] | int round[2][4] | int pc_so[2][T] | int pc_cnt[2][T] | int p_lo[T], p_hi[T]
+// ---------------------------------------------------------------------------------------------
+template <int NCW>
+__global__ void __launch_bounds__((NCW + 1) * 32) k_score_topk(const SearchArgs a) {
+    constexpr int NC = NCW * 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int T = a.T, stg = a.stage_postings, cap = a.cap;
+    float* sc = reinterpret_cast<float*>(smem_raw);
+    int32_t* st_ids = reinterpret_cast<int32_t*>(smem_raw + (size_t)a.tile_docs * 4);
+    float* st_w = reinterpret_cast<float*>(st_ids + 2 * stg);
+    u64* cand = reinterpret_cast<u64*>(st_w + 2 * stg);
+    u64* bar_full = cand + cap;
+    u64* bar_empty = bar_full + 2;
+    int* rd = reinterpret_cast<int*>(bar_empty + 2);  // [2][4] = {n_pieces, base, nd, tile_end}
+    int* pc_so = rd + 8;
+    int* pc_cnt = pc_so + 2 * T;
+    int* p_lo = pc_cnt + 2 * T;
+    int* p_hi = p_lo + T;
+    __shared__ int s_ncand, s_overflow;
     __shared__ u64 s_theta;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    const int warp = tid >> 5;
     const int q = blockIdx.x / a.splits;
     const int sp = blockIdx.x - q * a.splits;
     const int j0 = sp * a.tiles_per_split;
     const int j1 = min(a.n_tiles, j0 + a.tiles_per_split);
 
-    for (int i = tid * 4; i < a.tile_docs; i += kChunk)
+    for (int i = tid * 4; i < a.tile_docs; i += (NC + 32) * 4)
         *reinterpret_cast<float4*>(sc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid == 0) { s_ncand = 0; s_theta = a.theta0; }
-    u64 theta = a.theta0;
-    const int32_t* segq = a.seg + (int64_t)q * a.T * (a.n_tiles + 1);
+    if (tid == 0) {
+        s_ncand = 0;
+        s_overflow = 0;
+        s_theta = a.theta0;
+        mbar_init(bar_full + 0, 1);
+        mbar_init(bar_full + 1, 1);
+        mbar_init(bar_empty + 0, NCW);
+        mbar_init(bar_empty + 1, NCW);
+        mbar_fence_init();
+    }
     __syncthreads();
 
-    for (int j = j0; j < j1; ++j) {
-        const int base = j * a.tile_docs;
-        const int nd = min(a.tile_docs, a.n_docs - base);
-        for (int t = tid; t < a.T; t += kThreads) {
-            const int32_t* p = segq + (int64_t)t * (a.n_tiles + 1) + j;
-            s_lo[t] = __ldg(p);
-            s_hi[t] = __ldg(p + 1);
+    if (warp == NCW) {
+        // =============================== producer warp ========================================
+        const int32_t* segq = a.seg + (int64_t)q * (a.n_tiles + 1) * T;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = lane; t < T; t += 32) p_hi[t] = __ldg(segq + (int64_t)j0 * T + t);
+        for (int j = j0; j < j1; ++j) {
+            for (int t = lane; t < T; t += 32) {
+                p_lo[t] = p_hi[t];
+                p_hi[t] = __ldg(segq + (int64_t)(j + 1) * T + t);
+            }
+            __syncwarp();
+            int t = 0;
+            while (t < T && p_hi[t] <= p_lo[t]) ++t;
+            if (t == T && !a.general) continue;  // no posting of this query in the tile
+            int pos = (t < T) ? p_lo[t] : 0;
+            const int base = j * a.tile_docs;
+            const int nd = min(a.tile_docs, a.n_docs - base);
+            do {  // one round = one staging buffer
+                mbar_wait(bar_empty + stage, phase ^ 1);
+                int used = 0, np = 0;
+                uint32_t bytes = 0;
+                while (t < T) {
+                    const int room = stg - used;
+                    if (room < 8) break;
+                    const int a0 = pos & ~3;
+                    const int skip = pos - a0;
+                    const int take = min(p_hi[t] - pos, room - skip);
+                    const int ncopy = ((pos + take + 3) & ~3) - a0;
+                    if (lane == 0) {
+                        pc_so[stage * T + np] = used + skip;
+                        pc_cnt[stage * T + np] = take;
+                        bulk_copy_g2s(st_ids + stage * stg + used, a.ids + a0, (uint32_t)ncopy * 4u, bar_full + stage);
+                        bulk_copy_g2s(st_w + stage * stg + used, a.w + a0, (uint32_t)ncopy * 4u, bar_full + stage);
+                    }
+                    bytes += (uint32_t)ncopy * 8u;
+                    used += ncopy;
+                    ++np;
+                    pos += take;
+                    if (pos < p_hi[t]) break;  // buffer full, the term continues in the next round
+                    ++t;
+                    while (t < T && p_hi[t] <= p_lo[t]) ++t;
+                    if (t < T) pos = p_lo[t];
+                }
+                if (lane == 0) {
+                    rd[stage * 4 + 0] = np;
+                    rd[stage * 4 + 1] = base;
+                    rd[stage * 4 + 2] = nd;
+                    rd[stage * 4 + 3] = (t >= T) ? 1 : 0;
+                    mbar_arrive_expect_tx(bar_full + stage, bytes);
+                }
+                __syncwarp();
+                stage ^= 1;
+                if (stage == 0) phase ^= 1;
+            } while (t < T);
         }
-        __syncthreads();
+        mbar_wait(bar_empty + stage, phase ^ 1);
+        if (lane == 0) {
+            rd[stage * 4 + 0] = -1;  // end of stream
+            mbar_arrive(bar_full + stage);
+        }
+        return;
+    }
 
-        // ---- accumulate: terms strictly in query order, one fp32 add per posting -------------
-        for (int t = 0; t < a.T; ++t) {
-            const int lo = s_lo[t], hi = s_hi[t];
-            if (lo >= hi) continue;  // uniform
-            for (int i = lo + tid; i < hi; i += kChunk) {
-                const int i1 = i + kThreads, i2 = i + 2 * kThreads, i3 = i + 3 * kThreads;
-                const bool v1 = i1 < hi, v2 = i2 < hi, v3 = i3 < hi;
-                const int d0 = __ldg(a.ids + i);
-                const float w0 = __ldg(a.w + i);
-                int d1 = 0, d2 = 0, d3 = 0;
+    // ================================= consumer warps =========================================
+    const ConsumerGroup grp{NC, tid};
+    u64 theta = a.theta0;
+    float theta_f = (theta == 0ull) ? -INFINITY : fmaxf(key_score(theta), 1.401298464e-45f);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (;;) {
+        mbar_wait(bar_full + stage, phase);
+        const int np = rd[stage * 4 + 0];
+        if (np < 0) break;
+        const int base = rd[stage * 4 + 1];
+        const int nd = rd[stage * 4 + 2];
+        const int tile_end = rd[stage * 4 + 3];
+        const int32_t* sid = st_ids + stage * stg;
+        const float* sw = st_w + stage * stg;
+        // ---- accumulate the round's pieces: terms strictly in query order ---------------------
+        for (int i = 0; i < np; ++i) {
+            const int so = pc_so[stage * T + i];
+            const int cnt = pc_cnt[stage * T + i];
+            for (int e = tid; e < cnt; e += 4 * NC) {
+                const int e1 = e + NC, e2 = e + 2 * NC, e3 = e + 3 * NC;
+                const bool v1 = e1 < cnt, v2 = e2 < cnt, v3 = e3 < cnt;
+                const int d0 = sid[so + e];
+                const float w0 = sw[so + e];
+                int d1 = base, d2 = base, d3 = base;
                 float w1 = 0.f, w2 = 0.f, w3 = 0.f;
-                if (v1) { d1 = __ldg(a.ids + i1); w1 = __ldg(a.w + i1); }
-                if (v2) { d2 = __ldg(a.ids + i2); w2 = __ldg(a.w + i2); }
-                if (v3) { d3 = __ldg(a.ids + i3); w3 = __ldg(a.w + i3); }
+                if (v1) { d1 = sid[so + e1]; w1 = sw[so + e1]; }
+                if (v2) { d2 = sid[so + e2]; w2 = sw[so + e2]; }
+                if (v3) { d3 = sid[so + e3]; w3 = sw[so + e3]; }
                 sc[d0 - base] += w0;
                 if (v1) sc[d1 - base] += w1;
                 if (v2) sc[d2 - base] += w2;
                 if (v3) sc[d3 - base] += w3;
             }
-            __syncthreads();
+            grp.sync();
         }
+        if (lane == 0) mbar_arrive(bar_empty + stage);  // staging buffer may be refilled
+        stage ^= 1;
+        if (stage == 0) phase ^= 1;
+        if (!tile_end) continue;
 
-        if (kDenseOut) {
-            float* out = a.dense_out + (int64_t)q * a.n_docs + base;
-            for (int i = tid; i < nd; i += kThreads) { out[i] = sc[i]; sc[i] = 0.f; }
-            __syncthreads();
-            continue;
-        }
-
-        // ---- fused scan + zero: push every doc whose key beats the running k-th best ---------
-        for (int c0 = 0; c0 < nd; c0 += kChunk) {
-            const int idx = c0 + tid * 4;
-            const float4 v = *reinterpret_cast<const float4*>(sc + idx);
-            *reinterpret_cast<float4*>(sc + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
-            const uint32_t doc = (uint32_t)(base + idx);
-            const u64 k0 = make_key(v.x, doc), k1 = make_key(v.y, doc + 1);
-            const u64 k2 = make_key(v.z, doc + 2), k3 = make_key(v.w, doc + 3);
-            const bool p0 = (idx < nd) && k0 > theta, p1 = (idx + 1 < nd) && k1 > theta;
-            const bool p2 = (idx + 2 < nd) && k2 > theta, p3 = (idx + 3 < nd) && k3 > theta;
-            const int cnt = (int)p0 + (int)p1 + (int)p2 + (int)p3;
-            bool risk = false;
-            if (__ballot_sync(kFull, cnt > 0)) {
-                int incl = cnt;
+        // ---- fused scan + zero, no barriers: push the docs that beat the k-th best so far -----
+        for (;;) {
+            for (int idx = tid * 4; idx < nd; idx += NC * 4) {
+                float4 v = *reinterpret_cast<const float4*>(sc + idx);
+                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v.x >= theta_f || v.y >= theta_f || v.z >= theta_f || v.w >= theta_f) {
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+                    float zz[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(kFull, incl, o);
-                    if (lane >= o) incl += y;
+                    for (int e = 0; e < 4; ++e) {
+                        if (vv[e] >= theta_f && idx + e < nd) {
+                            const u64 key = make_key(vv[e], (uint32_t)(base + idx + e));
+                            if (key > theta) {
+                                const int pos = atomicAdd(&s_ncand, 1);
+                                if (pos < cap) cand[pos] = key;
+                                else { zz[e] = vv[e]; s_overflow = 1; }  // keep the score, rescan later
+                            }
+                        }
+                    }
+                    z = make_float4(zz[0], zz[1], zz[2], zz[3]);
                 }
-                const int total = __shfl_sync(kFull, incl, 31);
-                int wbase = 0;
-                if (lane == 31) wbase = atomicAdd(&s_ncand, total);
-                wbase = __shfl_sync(kFull, wbase, 31);
-                int pos = wbase + incl - cnt;
-                if (p0) cand[pos++] = k0;
-                if (p1) cand[pos++] = k1;
-                if (p2) cand[pos++] = k2;
-                if (p3) cand[pos++] = k3;
-                risk = (wbase + total > a.cap - kChunk);
+                *reinterpret_cast<float4*>(sc + idx) = z;
             }
-            if (__syncthreads_or(risk)) {
-                compact_candidates(cand, a.k, a.theta0, &s_ncand, &s_theta);
-                theta = s_theta;
-            }
+            grp.sync();  // tile scanned (and zeroed, except documents that did not fit)
+            if (!*reinterpret_cast<volatile int*>(&s_overflow)) break;
+            grp.sync();
+            if (tid == 0) s_overflow = 0;
+            compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
+            theta = s_theta;
+            theta_f = (theta == 0ull) ? -INFINITY : fmaxf(key_score(theta), 1.401298464e-45f);
         }
     }
 
-    if (kDenseOut) return;
-    compact_candidates(cand, a.k, a.theta0, &s_ncand, &s_theta);
+    grp.sync();
+    compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
     const int n = s_ncand;
     u64* out = a.partial + ((int64_t)q * a.splits + sp) * a.k;
-    for (int i = tid; i < a.k; i += kThreads) out[i] = (i < n) ? cand[i] : 0ull;
+    for (int i = tid; i < a.k; i += NC) out[i] = (i < n) ? cand[i] : 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -267,7 +444,7 @@ struct MergeArgs {
 };
 
 __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     u64* buf = reinterpret_cast<u64*>(smem_raw);
     unsigned char* present = reinterpret_cast<unsigned char*>(buf + a.P);
     const int tid = threadIdx.x;
@@ -295,7 +472,7 @@ __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
             buf[have + i] = key;
         }
         __syncthreads();
-        bitonic_sort_desc(buf, a.P);
+        bitonic_sort_desc(buf, a.P, CtaGroup{kThreads, tid});
         next += take;
         have = min(keep, a.P);
         if (take == 0) break;

@@ -12,7 +12,7 @@ from mojo_bm25_b200 import engine, synth
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workloads", default="B")
-ap.add_argument("--configs", default="0:0", help="comma list of tile_docs:splits")
+ap.add_argument("--configs", default="0:0:0:0", help="comma list of tile_docs:splits:consumer_warps:stage_postings")
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--scale", type=float, default=1.0)
 args = ap.parse_args()
@@ -27,9 +27,11 @@ for wl in args.workloads.split(","):
     print(f"# {wl}: docs={idx.n_docs} terms={idx.n_terms} nnz={idx.nnz} Q={q.shape[0]} T={q.shape[1]} k={k} "
           f"posting_bytes={pbytes/1e9:.3f} GB", flush=True)
     for cfg in args.configs.split(","):
-        tile, splits = (int(x) for x in cfg.split(":"))
+        tile, splits, warps, stage = (int(x) for x in (cfg.split(":") + ["0"] * 4)[:4])
         index.set_option("tile_docs", tile)
         index.set_option("splits", splits)
+        index.set_option("consumer_warps", warps)
+        index.set_option("stage_postings", stage)
         times = []
         for it in range(args.iters + 2):
             flush.zero_()
@@ -38,7 +40,7 @@ for wl in args.workloads.split(","):
         t = np.array(times[2:])
         seg, score, merge = np.median(t, axis=0)
         tot = seg + score + merge
-        print(json.dumps(dict(workload=wl, tile_docs=index.info.tile_docs, splits=splits, seg_ms=round(float(seg), 4),
+        print(json.dumps(dict(workload=wl, tile_docs=index.info.tile_docs, splits=splits, warps=warps, stage=stage, seg_ms=round(float(seg), 4),
                               score_ms=round(float(score), 4), merge_ms=round(float(merge), 4),
                               qps=round(q.shape[0] / tot * 1e3, 1), score_GBps=round(pbytes / score / 1e6, 1))), flush=True)
     index.close()
