@@ -158,7 +158,7 @@ struct bm25_index {
     std::vector<int32_t> h_indptr;  // host copy for byte accounting / validation
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
-    int opt_stage = 0, opt_warps = 0, opt_cap = 0;
+    int opt_stage = 0, opt_warps = 0, opt_cap = 0, opt_stages = 0, opt_sparse_pct = 0, opt_sparse_off = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace
@@ -170,13 +170,15 @@ struct bm25_index {
     PinnedBuf<int32_t> pin_queries, pin_out_ids;
     PinnedBuf<float> pin_out_scores;
     cudaStream_t own_stream = nullptr;
-    size_t smem_optin = 0;
+    size_t smem_optin = 0, smem_per_sm = 0;
 
+    int warps() const { return opt_warps > 0 ? opt_warps : 8; }
     int tile_docs() const {
-        int t = opt_tile_docs > 0 ? opt_tile_docs : 16384;
-        const int64_t need = std::max<int64_t>(((n_docs + 1023) / 1024) * 1024, 1024);
+        const int gran = 128 * warps();  // every consumer warp owns a stripe of whole 128-doc groups
+        int t = opt_tile_docs > 0 ? opt_tile_docs : 8192;
+        const int64_t need = std::max<int64_t>(((n_docs + gran - 1) / gran) * gran, gran);
         if (need < t) t = (int)need;
-        t = ((t + 1023) / 1024) * 1024;
+        t = ((t + gran - 1) / gran) * gran;
         return t;
     }
     int n_tiles() const { return (int)std::max<int64_t>(1, (n_docs + tile_docs() - 1) / tile_docs()); }
@@ -194,6 +196,7 @@ namespace {
 int finish_create(bm25_index* ix, const cudaDeviceProp& prop) {
     ix->sm_count = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
+    ix->smem_per_sm = prop.sharedMemPerMultiprocessor;
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     return BM25_OK;
 }
@@ -257,33 +260,43 @@ int canonicalise_host(const int32_t* indptr, const int32_t* indices, const float
 }
 
 struct LaunchPlan {
-    int tile_docs, n_tiles, splits, tiles_per_split, cap, stage, warps, general;
+    int tile_docs, n_tiles, splits, tiles_per_split, cap, stage, stages, warps, general, sparse_max;
     size_t smem;
     u64 theta0;
 };
 
-size_t score_smem(int tile_docs, int stage, int cap, int64_t T) {
-    return (size_t)tile_docs * 4 + (size_t)stage * 16 + (size_t)cap * 8 + 64 + (size_t)T * 24 + 128;
+// dynamic shared memory of k_score_topk (layout documented at the kernel)
+size_t score_smem(int tile_docs, int stage, int stages, int cap, int64_t T, int warps) {
+    return (size_t)tile_docs * 4 + (size_t)stages * stage * 8 + (size_t)cap * 8 + 3 * kMaxStages * 8 +
+           kMaxStages * 8 * 4 + (size_t)stages * T * 8 + (size_t)stages * T * (warps + 1) * 4 + (size_t)T * 8 + 128;
 }
 
 int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, bool dense, LaunchPlan* lp) {
+    lp->warps = ix->warps();
+    const int gran = 128 * lp->warps;
     lp->tile_docs = ix->tile_docs();
-    lp->warps = ix->opt_warps > 0 ? ix->opt_warps : 8;
     lp->stage = ix->opt_stage > 0 ? ((ix->opt_stage + 3) / 4) * 4 : 2048;
+    lp->stages = ix->opt_stages > 0 ? ix->opt_stages : 3;
     lp->cap = 0;
     if (!dense) {
         lp->cap = ix->opt_cap > 0 ? next_pow2(ix->opt_cap) : next_pow2(std::max(2 * (int64_t)k, (int64_t)512));
         if (lp->cap < k + 64) lp->cap = next_pow2((int64_t)k + 64);
     }
-    // shrink the tile until the CTA fits into shared memory
+    // Two CTAs per SM unless the caller pinned the shapes: shrink the staging ring first (it only
+    // hides latency), then the tile.
+    const bool pinned = ix->opt_tile_docs > 0 || ix->opt_stage > 0 || ix->opt_stages > 0;
+    const size_t hard = ix->smem_optin - 1024;
+    const size_t soft = pinned || dense ? hard : std::min(hard, (size_t)(ix->smem_per_sm / 2 - 2048));
     for (;;) {
         lp->smem = dense ? (size_t)lp->tile_docs * 4 + (size_t)T * 8 + 16
-                         : score_smem(lp->tile_docs, lp->stage, lp->cap, T);
-        if (lp->smem <= ix->smem_optin - 1024) break;
-        if (lp->tile_docs <= 1024)
-            return fail(BM25_ERR_UNSUPPORTED, "query shape (T=%lld, k=%d) does not fit in shared memory",
-                        (long long)T, k);
-        lp->tile_docs -= 1024;
+                         : score_smem(lp->tile_docs, lp->stage, lp->stages, lp->cap, T, lp->warps);
+        if (lp->smem <= soft) break;
+        if (!dense && !pinned && lp->stage > 1024) { lp->stage -= 512; continue; }
+        if (!dense && !pinned && lp->stages > 2) { lp->stages -= 1; continue; }
+        if (lp->tile_docs > gran && (lp->smem > hard || lp->tile_docs > 4096)) { lp->tile_docs -= gran; continue; }
+        if (lp->smem <= hard) break;
+        return fail(BM25_ERR_UNSUPPORTED, "query shape (T=%lld, k=%d) does not fit in shared memory",
+                    (long long)T, k);
     }
     lp->n_tiles = (int)std::max<int64_t>(1, (ix->n_docs + lp->tile_docs - 1) / lp->tile_docs);
     int splits = ix->opt_splits;
@@ -299,6 +312,8 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, bool dense, LaunchPla
     // k_merge; general index: every document competes (theta0 = 0 admits all keys).
     lp->theta0 = positive ? make_key(0.0f, 0u) : 0ull;
     lp->general = positive ? 0 : 1;
+    const int pct = ix->opt_sparse_pct > 0 ? ix->opt_sparse_pct : 25;
+    lp->sparse_max = ix->opt_sparse_off ? -1 : (int)((int64_t)lp->tile_docs * pct / 100);
     return BM25_OK;
 }
 
@@ -319,7 +334,7 @@ int launch_score_w(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, in
     static thread_local size_t configured[64] = {0};
     int rc = configure_smem(k_score_topk<NCW>, lp.smem, ix->smem_optin, &configured[ix->device % 64]);
     if (rc) return rc;
-    k_score_topk<NCW><<<(unsigned)grid, (NCW + 1) * 32, lp.smem, st>>>(a);
+    k_score_topk<NCW><<<(unsigned)grid, (NCW + 2) * 32, lp.smem, st>>>(a);
     return BM25_OK;
 }
 
@@ -413,6 +428,8 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.tiles_per_split = lp.tiles_per_split;
     a.cap = lp.cap;
     a.stage_postings = lp.stage;
+    a.n_stages = lp.stages;
+    a.sparse_max = lp.sparse_max;
     a.general = lp.general;
     if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
@@ -653,6 +670,14 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
         if (value != 0 && value != 4 && value != 8 && value != 16)
             return fail(BM25_ERR_INVALID, "consumer_warps must be 0, 4, 8 or 16");
         ix->opt_warps = (int)value;
+    } else if (!strcmp(name, "stages")) {
+        if (value != 0 && (value < 2 || value > kMaxStages)) return fail(BM25_ERR_INVALID, "stages must be 0 or 2..4");
+        ix->opt_stages = (int)value;
+    } else if (!strcmp(name, "sparse_pct")) {
+        if (value < 0 || value > 100) return fail(BM25_ERR_INVALID, "sparse_pct out of range");
+        ix->opt_sparse_pct = (int)value;
+    } else if (!strcmp(name, "sparse_off")) {
+        ix->opt_sparse_off = value ? 1 : 0;
     } else if (!strcmp(name, "cap")) {
         if (value < 0 || value > (1 << 14)) return fail(BM25_ERR_INVALID, "cap out of range");
         ix->opt_cap = (int)value;

@@ -151,6 +151,8 @@ struct SearchArgs {
     int n_docs, tile_docs, n_tiles;
     int splits, tiles_per_split, cap;
     int stage_postings;                   // capacity of one staging buffer (multiple of 4)
+    int n_stages;                         // staging ring depth (2..4)
+    int sparse_max;                       // tiles with at most this many postings use the sparse epilogue
     int general;                          // 1: zero-score docs compete (weights may be <= 0)
 };
 
@@ -224,34 +226,99 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_score_topk: the hot kernel.  CTA = (query, range of document tiles), warp-specialised:
+// k_score_topk (v3): the hot kernel.  CTA = (query, range of document tiles), warp-specialised,
+// no CTA-wide barrier on the steady-state path:
 //   producer warp : walks the tiles, packs the query terms' posting segments of a tile into
 //                   "rounds" that fit one staging buffer and issues them as 1-D bulk async copies
-//                   (TMA) into a 2-stage shared-memory ring, completion on mbarriers;
-//   consumer warps: wait for a round, add its pieces into the shared-memory score tile strictly
-//                   in query-term order (one fp32 add per posting, a named barrier between
-//                   terms -- a term has at most one posting per document, so no atomics), and at
-//                   the end of a tile run a barrier-free fused scan+zero that pushes only the
-//                   documents beating the running k-th best key into a candidate buffer.
+//                   (TMA, UBLKCP) into an NS-stage shared-memory ring; completion on mbarriers.
+//   searcher warp : for every staged piece longer than kFilterMax postings, binary-searches (in
+//                   shared memory) the boundaries of the NCW document stripes of the tile, then
+//                   hands the stage to the consumers (second mbarrier).
+//   consumer warps: warp w OWNS stripe w of the score tile (tile_docs / NCW documents).  It adds
+//                   the postings of its stripe, piece by piece in query-term order (one fp32 add
+//                   per posting; a term has at most one posting per document and every posting of
+//                   a document is handled by the same warp, so __syncwarp between pieces is the
+//                   only ordering needed -- no atomics, no named barriers).  Epilogue per tile:
+//                     sparse tile (all postings resident in one stage, few of them): re-walk the
+//                       staged postings, test the final score against the running k-th best,
+//                       push survivors into the candidate buffer and zero the touched slots;
+//                     dense tile: vectorised scan + zero of the warp's stripe.
+//                   The candidate buffer is shared by the CTA; when it overflows the consumers
+//                   meet at a (rare) named-barrier round, keep the k best and raise the threshold.
 // shared memory (dynamic):
-//   float score[tile_docs] | int32 st_ids[2][stg] | float st_w[2][stg] | u64 cand[cap]
-//   | u64 full[2], empty[2] | int round[2][4] | int pc_so[2][T] | int pc_cnt[2][T] | int p_lo[T], p_hi[T]
+//   float score[tile_docs] | int32 st_ids[NS][stg] | float st_w[NS][stg] | u64 cand[cap]
+//   | u64 full[4], ready[4], empty[4] | int rd[4][8] | int pc_so[NS][T] | int pc_cnt[NS][T]
+//   | int bnd[NS][T][NCW+1] | int p_lo[T], p_hi[T]
 // ---------------------------------------------------------------------------------------------
+constexpr int kFilterMax = 64;   // pieces up to this many postings are filtered, not searched
+constexpr int kMaxStages = 4;
+constexpr int kFlagTileEnd = 1, kFlagSparse = 2;
+
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+struct TopkState {
+    u64* cand;
+    int* s_ncand;
+    int* s_overflow;
+    int cap;
+    u64 theta;      // key must be > theta to compete
+    float theta_f;  // cheap pre-filter on the raw score
+    __device__ __forceinline__ void set_theta(u64 t) {
+        theta = t;
+        theta_f = (t == 0ull) ? -INFINITY : fmaxf(key_score(t), 1.401298464e-45f);
+    }
+    // returns false when the candidate buffer is full (the caller keeps the score in place)
+    __device__ __forceinline__ bool push(float v, uint32_t doc) {
+        const u64 key = make_key(v, doc);
+        if (key > theta) {
+            const int pos = atomicAdd(s_ncand, 1);
+            if (pos < cap) cand[pos] = key;
+            else { *reinterpret_cast<volatile int*>(s_overflow) = 1; return false; }
+        }
+        return true;
+    }
+};
+
+// vectorised scan + zero of one warp's stripe (S documents, the first nd_w of them real)
+__device__ __forceinline__ bool stripe_scan(float* scw, int S, int nd_w, uint32_t doc0, int lane, TopkState& tk) {
+    bool left = false;
+#pragma unroll 2
+    for (int idx = lane * 4; idx < S; idx += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(scw + idx);
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v.x >= tk.theta_f || v.y >= tk.theta_f || v.z >= tk.theta_f || v.w >= tk.theta_f) {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            float zz[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (vv[e] >= tk.theta_f && idx + e < nd_w) {
+                    if (!tk.push(vv[e], doc0 + (uint32_t)(idx + e))) { zz[e] = vv[e]; left = true; }
+                }
+            }
+            z = make_float4(zz[0], zz[1], zz[2], zz[3]);
+        }
+        *reinterpret_cast<float4*>(scw + idx) = z;
+    }
+    return left;
+}
+
 template <int NCW>
-__global__ void __launch_bounds__((NCW + 1) * 32) k_score_topk(const SearchArgs a) {
+__global__ void __launch_bounds__((NCW + 2) * 32) k_score_topk(const SearchArgs a) {
     constexpr int NC = NCW * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int T = a.T, stg = a.stage_postings, cap = a.cap;
+    const int T = a.T, stg = a.stage_postings, cap = a.cap, NS = a.n_stages;
     float* sc = reinterpret_cast<float*>(smem_raw);
     int32_t* st_ids = reinterpret_cast<int32_t*>(smem_raw + (size_t)a.tile_docs * 4);
-    float* st_w = reinterpret_cast<float*>(st_ids + 2 * stg);
-    u64* cand = reinterpret_cast<u64*>(st_w + 2 * stg);
+    float* st_w = reinterpret_cast<float*>(st_ids + NS * stg);
+    u64* cand = reinterpret_cast<u64*>(st_w + NS * stg);
     u64* bar_full = cand + cap;
-    u64* bar_empty = bar_full + 2;
-    int* rd = reinterpret_cast<int*>(bar_empty + 2);  // [2][4] = {n_pieces, base, nd, tile_end}
-    int* pc_so = rd + 8;
-    int* pc_cnt = pc_so + 2 * T;
-    int* p_lo = pc_cnt + 2 * T;
+    u64* bar_ready = bar_full + kMaxStages;
+    u64* bar_empty = bar_ready + kMaxStages;
+    int* rd = reinterpret_cast<int*>(bar_empty + kMaxStages);  // [4][8] = {n_pieces, base, nd, flags}
+    int* pc_so = rd + kMaxStages * 8;
+    int* pc_cnt = pc_so + NS * T;
+    int* bnd = pc_cnt + NS * T;
+    int* p_lo = bnd + NS * T * (NCW + 1);
     int* p_hi = p_lo + T;
     __shared__ int s_ncand, s_overflow;
     __shared__ u64 s_theta;
@@ -263,17 +330,19 @@ __global__ void __launch_bounds__((NCW + 1) * 32) k_score_topk(const SearchArgs 
     const int sp = blockIdx.x - q * a.splits;
     const int j0 = sp * a.tiles_per_split;
     const int j1 = min(a.n_tiles, j0 + a.tiles_per_split);
+    const int S = a.tile_docs / NCW;  // documents per consumer stripe (multiple of 128)
 
-    for (int i = tid * 4; i < a.tile_docs; i += (NC + 32) * 4)
+    for (int i = tid * 4; i < a.tile_docs; i += (NC + 64) * 4)
         *reinterpret_cast<float4*>(sc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         s_ncand = 0;
         s_overflow = 0;
         s_theta = a.theta0;
-        mbar_init(bar_full + 0, 1);
-        mbar_init(bar_full + 1, 1);
-        mbar_init(bar_empty + 0, NCW);
-        mbar_init(bar_empty + 1, NCW);
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(bar_full + s, 1);
+            mbar_init(bar_ready + s, 32);
+            mbar_init(bar_empty + s, NCW);
+        }
         mbar_fence_init();
     }
     __syncthreads();
@@ -285,17 +354,31 @@ __global__ void __launch_bounds__((NCW + 1) * 32) k_score_topk(const SearchArgs 
         uint32_t phase = 0;
         for (int t = lane; t < T; t += 32) p_hi[t] = __ldg(segq + (int64_t)j0 * T + t);
         for (int j = j0; j < j1; ++j) {
+            int tot = 0, npost = 0;
             for (int t = lane; t < T; t += 32) {
-                p_lo[t] = p_hi[t];
-                p_hi[t] = __ldg(segq + (int64_t)(j + 1) * T + t);
+                const int lo = p_hi[t];
+                const int hi = __ldg(segq + (int64_t)(j + 1) * T + t);
+                p_lo[t] = lo;
+                p_hi[t] = hi;
+                if (hi > lo) {
+                    tot += ((hi + 3) & ~3) - (lo & ~3);
+                    npost += hi - lo;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                tot += __shfl_xor_sync(kFull, tot, o);
+                npost += __shfl_xor_sync(kFull, npost, o);
             }
             __syncwarp();
+            if (npost == 0 && !a.general) continue;  // no posting of this query in the tile
             int t = 0;
             while (t < T && p_hi[t] <= p_lo[t]) ++t;
-            if (t == T && !a.general) continue;  // no posting of this query in the tile
             int pos = (t < T) ? p_lo[t] : 0;
             const int base = j * a.tile_docs;
             const int nd = min(a.tile_docs, a.n_docs - base);
+            // sparse epilogue only when the whole tile is resident in ONE round (tot + 8 <= stg guarantees it)
+            const int sparse = (!a.general && tot + 8 <= stg && npost <= a.sparse_max) ? kFlagSparse : 0;
             do {  // one round = one staging buffer
                 mbar_wait(bar_empty + stage, phase ^ 1);
                 int used = 0, np = 0;
@@ -308,7 +391,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32) k_score_topk(const SearchArgs 
                     const int take = min(p_hi[t] - pos, room - skip);
                     const int ncopy = ((pos + take + 3) & ~3) - a0;
                     if (lane == 0) {
-                        pc_so[stage * T + np] = used + skip;
+                        pc_so[stage * T + np] = stage * stg + used + skip;
                         pc_cnt[stage * T + np] = take;
                         bulk_copy_g2s(st_ids + stage * stg + used, a.ids + a0, (uint32_t)ncopy * 4u, bar_full + stage);
                         bulk_copy_g2s(st_w + stage * stg + used, a.w + a0, (uint32_t)ncopy * 4u, bar_full + stage);
@@ -323,100 +406,195 @@ __global__ void __launch_bounds__((NCW + 1) * 32) k_score_topk(const SearchArgs 
                     if (t < T) pos = p_lo[t];
                 }
                 if (lane == 0) {
-                    rd[stage * 4 + 0] = np;
-                    rd[stage * 4 + 1] = base;
-                    rd[stage * 4 + 2] = nd;
-                    rd[stage * 4 + 3] = (t >= T) ? 1 : 0;
+                    rd[stage * 8 + 0] = np;
+                    rd[stage * 8 + 1] = base;
+                    rd[stage * 8 + 2] = nd;
+                    rd[stage * 8 + 3] = ((t >= T) ? kFlagTileEnd : 0) | sparse;
                     mbar_arrive_expect_tx(bar_full + stage, bytes);
                 }
                 __syncwarp();
-                stage ^= 1;
-                if (stage == 0) phase ^= 1;
+                if (++stage == NS) { stage = 0; phase ^= 1; }
             } while (t < T);
         }
         mbar_wait(bar_empty + stage, phase ^ 1);
         if (lane == 0) {
-            rd[stage * 4 + 0] = -1;  // end of stream
+            rd[stage * 8 + 0] = -1;  // end of stream
             mbar_arrive(bar_full + stage);
         }
         return;
     }
 
-    // ================================= consumer warps =========================================
-    const ConsumerGroup grp{NC, tid};
-    u64 theta = a.theta0;
-    float theta_f = (theta == 0ull) ? -INFINITY : fmaxf(key_score(theta), 1.401298464e-45f);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (;;) {
-        mbar_wait(bar_full + stage, phase);
-        const int np = rd[stage * 4 + 0];
-        if (np < 0) break;
-        const int base = rd[stage * 4 + 1];
-        const int nd = rd[stage * 4 + 2];
-        const int tile_end = rd[stage * 4 + 3];
-        const int32_t* sid = st_ids + stage * stg;
-        const float* sw = st_w + stage * stg;
-        // ---- accumulate the round's pieces: terms strictly in query order ---------------------
-        for (int i = 0; i < np; ++i) {
-            const int so = pc_so[stage * T + i];
-            const int cnt = pc_cnt[stage * T + i];
-            for (int e = tid; e < cnt; e += 4 * NC) {
-                const int e1 = e + NC, e2 = e + 2 * NC, e3 = e + 3 * NC;
-                const bool v1 = e1 < cnt, v2 = e2 < cnt, v3 = e3 < cnt;
-                const int d0 = sid[so + e];
-                const float w0 = sw[so + e];
-                int d1 = base, d2 = base, d3 = base;
-                float w1 = 0.f, w2 = 0.f, w3 = 0.f;
-                if (v1) { d1 = sid[so + e1]; w1 = sw[so + e1]; }
-                if (v2) { d2 = sid[so + e2]; w2 = sw[so + e2]; }
-                if (v3) { d3 = sid[so + e3]; w3 = sw[so + e3]; }
-                sc[d0 - base] += w0;
-                if (v1) sc[d1 - base] += w1;
-                if (v2) sc[d2 - base] += w2;
-                if (v3) sc[d3 - base] += w3;
-            }
-            grp.sync();
-        }
-        if (lane == 0) mbar_arrive(bar_empty + stage);  // staging buffer may be refilled
-        stage ^= 1;
-        if (stage == 0) phase ^= 1;
-        if (!tile_end) continue;
-
-        // ---- fused scan + zero, no barriers: push the docs that beat the k-th best so far -----
+    if (warp == NCW + 1) {
+        // =============================== searcher warp ========================================
+        int stage = 0;
+        uint32_t phase = 0;
         for (;;) {
-            for (int idx = tid * 4; idx < nd; idx += NC * 4) {
-                float4 v = *reinterpret_cast<const float4*>(sc + idx);
-                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (v.x >= theta_f || v.y >= theta_f || v.z >= theta_f || v.w >= theta_f) {
-                    const float vv[4] = {v.x, v.y, v.z, v.w};
-                    float zz[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (vv[e] >= theta_f && idx + e < nd) {
-                            const u64 key = make_key(vv[e], (uint32_t)(base + idx + e));
-                            if (key > theta) {
-                                const int pos = atomicAdd(&s_ncand, 1);
-                                if (pos < cap) cand[pos] = key;
-                                else { zz[e] = vv[e]; s_overflow = 1; }  // keep the score, rescan later
-                            }
+            mbar_wait(bar_full + stage, phase);
+            const int np = rd[stage * 8 + 0];
+            if (np > 0) {
+                const int base = rd[stage * 8 + 1];
+                const int total = np * (NCW + 1);
+                for (int idx = lane; idx < total; idx += 32) {
+                    const int i = idx / (NCW + 1);
+                    const int b = idx - i * (NCW + 1);
+                    const int cnt = pc_cnt[stage * T + i];
+                    if (cnt <= kFilterMax) continue;
+                    const int so = pc_so[stage * T + i];
+                    int lo = 0, hi = cnt;
+                    if (b == 0) hi = 0;
+                    else if (b == NCW) lo = cnt;
+                    else {
+                        const int target = base + b * S;
+                        const int32_t* p = st_ids + so;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (p[mid] < target) lo = mid + 1; else hi = mid;
                         }
                     }
-                    z = make_float4(zz[0], zz[1], zz[2], zz[3]);
+                    bnd[(stage * T + i) * (NCW + 1) + b] = so + lo;
                 }
-                *reinterpret_cast<float4*>(sc + idx) = z;
             }
-            grp.sync();  // tile scanned (and zeroed, except documents that did not fit)
-            if (!*reinterpret_cast<volatile int*>(&s_overflow)) break;
-            grp.sync();
-            if (tid == 0) s_overflow = 0;
-            compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
-            theta = s_theta;
-            theta_f = (theta == 0ull) ? -INFINITY : fmaxf(key_score(theta), 1.401298464e-45f);
+            mbar_arrive(bar_ready + stage);  // all 32 lanes arrive (release of the bnd writes)
+            if (np < 0) return;
+            if (++stage == NS) { stage = 0; phase ^= 1; }
         }
     }
 
-    grp.sync();
+    // ================================= consumer warps =========================================
+    const ConsumerGroup grp{NC, tid};
+    TopkState tk{cand, &s_ncand, &s_overflow, cap, 0ull, 0.f};
+    tk.set_theta(a.theta0);
+    float* scw = sc + warp * S;
+    bool leftover = false;       // this warp's stripe still holds scores that did not fit in cand
+    uint32_t left_doc0 = 0;
+    int left_nd = 0;
+
+    // candidate-buffer overflow round: every consumer warp takes part (see the protocol above)
+    auto overflow_round = [&]() {
+        for (;;) {
+            compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
+            if (tid == 0) s_overflow = 0;
+            grp.sync();
+            tk.set_theta(s_theta);
+            if (leftover) leftover = __any_sync(kFull, stripe_scan(scw, S, left_nd, left_doc0, lane, tk));
+            grp.sync();
+            const int again = ld_volatile(&s_overflow);
+            grp.sync();
+            if (!again) break;
+        }
+    };
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (;;) {
+        mbar_wait(bar_ready + stage, phase);
+        mbar_wait(bar_full + stage, phase);  // already complete; orders the bulk-copy writes for this thread
+        const int np = rd[stage * 8 + 0];
+        if (np < 0) break;
+        const int base = rd[stage * 8 + 1];
+        const int nd = rd[stage * 8 + 2];
+        const int flags = rd[stage * 8 + 3];
+        const int sbase = base + warp * S;  // first document of this warp's stripe
+        // ---- accumulate the round's pieces: terms strictly in query order ---------------------
+        for (int i = 0; i < np; ++i) {
+            const int cnt = pc_cnt[stage * T + i];
+            const int so = pc_so[stage * T + i];
+            if (cnt <= kFilterMax) {
+                for (int e = so + lane; e < so + cnt; e += 32) {
+                    const unsigned d = (unsigned)(st_ids[e] - sbase);
+                    if (d < (unsigned)S) scw[d] += st_w[e];
+                }
+            } else {
+                const int lo = bnd[(stage * T + i) * (NCW + 1) + warp];
+                const int hi = bnd[(stage * T + i) * (NCW + 1) + warp + 1];
+                for (int e = lo + lane; e < hi; e += 128) {
+                    const bool v1 = e + 32 < hi, v2 = e + 64 < hi, v3 = e + 96 < hi;
+                    const int i0 = st_ids[e] - sbase;
+                    const int i1 = v1 ? st_ids[e + 32] - sbase : 0;
+                    const int i2 = v2 ? st_ids[e + 64] - sbase : 0;
+                    const int i3 = v3 ? st_ids[e + 96] - sbase : 0;
+                    const float w0 = st_w[e];
+                    const float w1 = v1 ? st_w[e + 32] : 0.f;
+                    const float w2 = v2 ? st_w[e + 64] : 0.f;
+                    const float w3 = v3 ? st_w[e + 96] : 0.f;
+                    // one term has at most one posting per document: the four slots are distinct
+                    const float s0 = scw[i0];
+                    const float s1 = v1 ? scw[i1] : 0.f;
+                    const float s2 = v2 ? scw[i2] : 0.f;
+                    const float s3 = v3 ? scw[i3] : 0.f;
+                    scw[i0] = s0 + w0;
+                    if (v1) scw[i1] = s1 + w1;
+                    if (v2) scw[i2] = s2 + w2;
+                    if (v3) scw[i3] = s3 + w3;
+                }
+            }
+            __syncwarp();
+        }
+        bool left = false;
+        const bool sparse = (flags & (kFlagSparse | kFlagTileEnd)) == (kFlagSparse | kFlagTileEnd);
+        if (sparse) {
+            // ---- sparse epilogue: re-walk the staged postings, test + zero the touched slots ---
+            for (int i = 0; i < np; ++i) {
+                const int cnt = pc_cnt[stage * T + i];
+                const int so = pc_so[stage * T + i];
+                if (cnt <= kFilterMax) {
+                    for (int e = so + lane; e < so + cnt; e += 32) {
+                        const unsigned d = (unsigned)(st_ids[e] - sbase);
+                        if (d < (unsigned)S) {
+                            const float v = scw[d];
+                            if (v >= tk.theta_f && !tk.push(v, (uint32_t)sbase + d)) left = true;
+                            else scw[d] = 0.f;
+                        }
+                    }
+                } else {
+                    const int lo = bnd[(stage * T + i) * (NCW + 1) + warp];
+                    const int hi = bnd[(stage * T + i) * (NCW + 1) + warp + 1];
+                    for (int e = lo + lane; e < hi; e += 128) {
+                        const bool v1 = e + 32 < hi, v2 = e + 64 < hi, v3 = e + 96 < hi;
+                        const int i0 = st_ids[e] - sbase;
+                        const int i1 = v1 ? st_ids[e + 32] - sbase : i0;
+                        const int i2 = v2 ? st_ids[e + 64] - sbase : i0;
+                        const int i3 = v3 ? st_ids[e + 96] - sbase : i0;
+                        const float s0 = scw[i0], s1 = scw[i1], s2 = scw[i2], s3 = scw[i3];
+                        bool k0 = false, k1 = false, k2 = false, k3 = false;  // keep (buffer full)
+                        if (s0 >= tk.theta_f) k0 = !tk.push(s0, (uint32_t)(sbase + i0));
+                        if (v1 && s1 >= tk.theta_f) k1 = !tk.push(s1, (uint32_t)(sbase + i1));
+                        if (v2 && s2 >= tk.theta_f) k2 = !tk.push(s2, (uint32_t)(sbase + i2));
+                        if (v3 && s3 >= tk.theta_f) k3 = !tk.push(s3, (uint32_t)(sbase + i3));
+                        if (!k0) scw[i0] = 0.f;
+                        if (v1 && !k1) scw[i1] = 0.f;
+                        if (v2 && !k2) scw[i2] = 0.f;
+                        if (v3 && !k3) scw[i3] = 0.f;
+                        left |= k0 | k1 | k2 | k3;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + stage);  // staging buffer may be refilled
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+        if (flags & kFlagTileEnd) {
+            const int nd_w = min(max(nd - warp * S, 0), S);
+            if (!sparse) left = stripe_scan(scw, S, nd_w, (uint32_t)sbase, lane, tk);
+            if (__any_sync(kFull, left)) {
+                leftover = true;
+                left_doc0 = (uint32_t)sbase;
+                left_nd = nd_w;
+            }
+        }
+        // checked after EVERY round (not only at tile ends): a warp that is ahead in the ring must be
+        // able to join the barrier without waiting for a stage the blocked warps have not released
+        if (leftover || ld_volatile(&s_overflow)) {
+            grp.sync();
+            overflow_round();
+        }
+    }
+    for (;;) {  // finished: keep serving overflow rounds until every consumer warp is here
+        grp.sync();
+        if (!ld_volatile(&s_overflow)) break;
+        overflow_round();
+    }
     compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
     const int n = s_ncand;
     u64* out = a.partial + ((int64_t)q * a.splits + sp) * a.k;

@@ -12,7 +12,8 @@ from mojo_bm25_b200 import engine, synth
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workloads", default="B")
-ap.add_argument("--configs", default="0:0:0:0", help="comma list of tile_docs:splits:consumer_warps:stage_postings")
+ap.add_argument("--configs", default="default", help="comma list of option sets, each 'name=value:name=value' "
+                "(bm25_index_set_option names: tile_docs, splits, consumer_warps, stage_postings, stages, cap, sparse_pct, sparse_off)")
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--scale", type=float, default=1.0)
 args = ap.parse_args()
@@ -27,11 +28,13 @@ for wl in args.workloads.split(","):
     print(f"# {wl}: docs={idx.n_docs} terms={idx.n_terms} nnz={idx.nnz} Q={q.shape[0]} T={q.shape[1]} k={k} "
           f"posting_bytes={pbytes/1e9:.3f} GB", flush=True)
     for cfg in args.configs.split(","):
-        tile, splits, warps, stage = (int(x) for x in (cfg.split(":") + ["0"] * 4)[:4])
-        index.set_option("tile_docs", tile)
-        index.set_option("splits", splits)
-        index.set_option("consumer_warps", warps)
-        index.set_option("stage_postings", stage)
+        opts = dict(tile_docs=0, splits=0, consumer_warps=0, stage_postings=0, stages=0, cap=0, sparse_pct=0, sparse_off=0)
+        if cfg != "default":
+            for kv in cfg.split(":"):
+                name, val = kv.split("=")
+                opts[name] = int(val)
+        for name, val in opts.items():
+            index.set_option(name, val)
         times = []
         for it in range(args.iters + 2):
             flush.zero_()
@@ -40,7 +43,7 @@ for wl in args.workloads.split(","):
         t = np.array(times[2:])
         seg, score, merge = np.median(t, axis=0)
         tot = seg + score + merge
-        print(json.dumps(dict(workload=wl, tile_docs=index.info.tile_docs, splits=splits, warps=warps, stage=stage, seg_ms=round(float(seg), 4),
+        print(json.dumps(dict(workload=wl, cfg=cfg, tile_docs=index.info.tile_docs, seg_ms=round(float(seg), 4),
                               score_ms=round(float(score), 4), merge_ms=round(float(merge), 4),
                               qps=round(q.shape[0] / tot * 1e3, 1), score_GBps=round(pbytes / score / 1e6, 1))), flush=True)
     index.close()
