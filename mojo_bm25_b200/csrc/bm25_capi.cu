@@ -158,13 +158,13 @@ struct bm25_index {
     std::vector<int32_t> h_indptr;  // host copy for byte accounting / validation
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
-    int opt_stage = 0, opt_warps = 0, opt_cap = 0, opt_stages = 0, opt_sparse_pct = 0, opt_sparse_off = 0;
+    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace
     std::mutex mu;
     DevBuf<int32_t> ws_seg;
-    DevBuf<u64> ws_partial;
+    DevBuf<u64> ws_partial, ws_theta;
     DevBuf<int32_t> ws_queries, ws_out_ids;
     DevBuf<float> ws_out_scores;
     PinnedBuf<int32_t> pin_queries, pin_out_ids;
@@ -173,19 +173,17 @@ struct bm25_index {
     size_t smem_optin = 0, smem_per_sm = 0;
 
     int warps() const { return opt_warps > 0 ? opt_warps : 8; }
-    int tile_docs() const {
-        const int gran = 128 * warps();  // every consumer warp owns a stripe of whole 128-doc groups
-        int t = opt_tile_docs > 0 ? opt_tile_docs : 8192;
-        const int64_t need = std::max<int64_t>(((n_docs + gran - 1) / gran) * gran, gran);
+    int tile_docs() const {  // S: documents per warp tile (multiple of 128)
+        int t = opt_tile_docs > 0 ? opt_tile_docs : 2048;
+        const int64_t need = std::max<int64_t>(((n_docs + 127) / 128) * 128, 128);
         if (need < t) t = (int)need;
-        t = ((t + gran - 1) / gran) * gran;
-        return t;
+        return ((t + 127) / 128) * 128;
     }
     int n_tiles() const { return (int)std::max<int64_t>(1, (n_docs + tile_docs() - 1) / tile_docs()); }
     int64_t device_bytes() const {
         int64_t b = 0;
         if (!borrowed) b += (n_terms + 1) * 4 + nnz * 8;
-        b += ws_seg.bytes() + ws_partial.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
+        b += ws_seg.bytes() + ws_partial.bytes() + ws_theta.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
              ws_out_scores.bytes();
         return b;
     }
@@ -260,60 +258,82 @@ int canonicalise_host(const int32_t* indptr, const int32_t* indices, const float
 }
 
 struct LaunchPlan {
-    int tile_docs, n_tiles, splits, tiles_per_split, cap, stage, stages, warps, general, sparse_max;
+    int tile_docs, n_tiles, splits, tiles_per_split, cap, warps, general;
+    int tiles_per_chunk, n_chunks;  // k_score_topk: a chunk = the tiles one warp walks
+    int seg_docs, seg_rows;         // granularity / row count of the segment table
     size_t smem;
     u64 theta0;
 };
 
 // dynamic shared memory of k_score_topk (layout documented at the kernel)
-size_t score_smem(int tile_docs, int stage, int stages, int cap, int64_t T, int warps) {
-    return (size_t)tile_docs * 4 + (size_t)stages * stage * 8 + (size_t)cap * 8 + 3 * kMaxStages * 8 +
-           kMaxStages * 8 * 4 + (size_t)stages * T * 8 + (size_t)stages * T * (warps + 1) * 4 + (size_t)T * 8 + 128;
+size_t score_smem(int tile_docs, int cap, int64_t T, int warps) {
+    return (size_t)warps * tile_docs * 4 + (size_t)cap * 8 + (size_t)warps * T * 12 + 128;
 }
 
-int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, bool dense, LaunchPlan* lp) {
-    lp->warps = ix->warps();
-    const int gran = 128 * lp->warps;
-    lp->tile_docs = ix->tile_docs();
-    lp->stage = ix->opt_stage > 0 ? ((ix->opt_stage + 3) / 4) * 4 : 2048;
-    lp->stages = ix->opt_stages > 0 ? ix->opt_stages : 3;
-    lp->cap = 0;
-    if (!dense) {
-        lp->cap = ix->opt_cap > 0 ? next_pow2(ix->opt_cap) : next_pow2(std::max(2 * (int64_t)k, (int64_t)512));
-        if (lp->cap < k + 64) lp->cap = next_pow2((int64_t)k + 64);
-    }
-    // Two CTAs per SM unless the caller pinned the shapes: shrink the staging ring first (it only
-    // hides latency), then the tile.
-    const bool pinned = ix->opt_tile_docs > 0 || ix->opt_stage > 0 || ix->opt_stages > 0;
-    const size_t hard = ix->smem_optin - 1024;
-    const size_t soft = pinned || dense ? hard : std::min(hard, (size_t)(ix->smem_per_sm / 2 - 2048));
-    for (;;) {
-        lp->smem = dense ? (size_t)lp->tile_docs * 4 + (size_t)T * 8 + 16
-                         : score_smem(lp->tile_docs, lp->stage, lp->stages, lp->cap, T, lp->warps);
-        if (lp->smem <= soft) break;
-        if (!dense && !pinned && lp->stage > 1024) { lp->stage -= 512; continue; }
-        if (!dense && !pinned && lp->stages > 2) { lp->stages -= 1; continue; }
-        if (lp->tile_docs > gran && (lp->smem > hard || lp->tile_docs > 4096)) { lp->tile_docs -= gran; continue; }
-        if (lp->smem <= hard) break;
-        return fail(BM25_ERR_UNSUPPORTED, "query shape (T=%lld, k=%d) does not fit in shared memory",
-                    (long long)T, k);
-    }
-    lp->n_tiles = (int)std::max<int64_t>(1, (ix->n_docs + lp->tile_docs - 1) / lp->tile_docs);
-    int splits = ix->opt_splits;
-    if (splits <= 0) {
-        const int64_t slots = (int64_t)ix->sm_count * 2 * 4;
-        splits = (int)std::max<int64_t>(1, (slots + Q - 1) / std::max<int64_t>(Q, 1));
-    }
-    splits = std::max(1, std::min(splits, lp->n_tiles));
-    lp->tiles_per_split = (lp->n_tiles + splits - 1) / splits;
-    lp->splits = (lp->n_tiles + lp->tiles_per_split - 1) / lp->tiles_per_split;
+void plan_mode(const bm25_index* ix, LaunchPlan* lp) {
     const bool positive = ix->all_positive && !ix->opt_force_general;
     // positive index: only strictly positive scores compete, zero-score docs are filled in by
     // k_merge; general index: every document competes (theta0 = 0 admits all keys).
     lp->theta0 = positive ? make_key(0.0f, 0u) : 0ull;
     lp->general = positive ? 0 : 1;
-    const int pct = ix->opt_sparse_pct > 0 ? ix->opt_sparse_pct : 25;
-    lp->sparse_max = ix->opt_sparse_off ? -1 : (int)((int64_t)lp->tile_docs * pct / 100);
+}
+
+// k_scores_dense (parity/debug): CTA = (query, range of 16K-document tiles)
+int make_plan_dense(bm25_index* ix, int64_t Q, int64_t T, LaunchPlan* lp) {
+    *lp = LaunchPlan{};
+    lp->warps = kThreads / 32;
+    int t = 16384;
+    const int64_t need = std::max<int64_t>(((ix->n_docs + 1023) / 1024) * 1024, 1024);
+    if (need < t) t = (int)need;
+    lp->tile_docs = t;
+    lp->smem = (size_t)lp->tile_docs * 4 + (size_t)T * 8 + 16;
+    if (lp->smem > ix->smem_optin - 1024)
+        return fail(BM25_ERR_UNSUPPORTED, "query width T=%lld does not fit in shared memory", (long long)T);
+    lp->n_tiles = (int)std::max<int64_t>(1, (ix->n_docs + lp->tile_docs - 1) / lp->tile_docs);
+    const int64_t slots = (int64_t)ix->sm_count * 2 * 4;
+    int splits = (int)std::max<int64_t>(1, (slots + Q - 1) / std::max<int64_t>(Q, 1));
+    splits = std::max(1, std::min(splits, lp->n_tiles));
+    lp->tiles_per_split = (lp->n_tiles + splits - 1) / splits;
+    lp->splits = (lp->n_tiles + lp->tiles_per_split - 1) / lp->tiles_per_split;
+    lp->seg_docs = lp->tile_docs;
+    lp->seg_rows = lp->n_tiles;
+    plan_mode(ix, lp);
+    return BM25_OK;
+}
+
+int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
+    *lp = LaunchPlan{};
+    lp->warps = ix->warps();
+    lp->tile_docs = ix->tile_docs();
+    lp->cap = ix->opt_cap > 0 ? next_pow2(ix->opt_cap) : next_pow2(std::max(2 * (int64_t)k, (int64_t)512));
+    if (lp->cap < k + 64) lp->cap = next_pow2((int64_t)k + 64);
+    // shrink the CTA (fewer warps, then smaller tiles) until it fits into shared memory
+    const size_t hard = ix->smem_optin - 1024;
+    for (;;) {
+        lp->smem = score_smem(lp->tile_docs, lp->cap, T, lp->warps);
+        if (lp->smem <= hard) break;
+        if (lp->warps > 4) { lp->warps -= 1; continue; }
+        if (lp->tile_docs > 512) { lp->tile_docs -= 128; continue; }
+        return fail(BM25_ERR_UNSUPPORTED, "query shape (T=%lld, k=%d) does not fit in shared memory",
+                    (long long)T, k);
+    }
+    lp->n_tiles = (int)std::max<int64_t>(1, (ix->n_docs + lp->tile_docs - 1) / lp->tile_docs);
+    const int max_splits = (lp->n_tiles + lp->warps - 1) / lp->warps;  // one tile per warp
+    int splits = ix->opt_splits;
+    if (splits <= 0) {
+        const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>((int64_t)(ix->smem_per_sm - 1024) / (int64_t)(lp->smem + 1024),
+                                                                      2048 / (lp->warps * 32)));
+        const int64_t waves = ix->opt_waves > 0 ? ix->opt_waves : 6;
+        const int64_t want = waves * per_sm * ix->sm_count;  // CTAs in flight x waves
+        splits = (int)std::max<int64_t>(1, (want + Q - 1) / std::max<int64_t>(Q, 1));
+    }
+    splits = std::max(1, std::min(splits, max_splits));
+    lp->tiles_per_chunk = (lp->n_tiles + splits * lp->warps - 1) / (splits * lp->warps);
+    lp->n_chunks = (lp->n_tiles + lp->tiles_per_chunk - 1) / lp->tiles_per_chunk;
+    lp->splits = (lp->n_chunks + lp->warps - 1) / lp->warps;
+    lp->seg_docs = lp->tiles_per_chunk * lp->tile_docs;
+    lp->seg_rows = lp->n_chunks;
+    plan_mode(ix, lp);
     return BM25_OK;
 }
 
@@ -329,15 +349,6 @@ int configure_smem(Kern kern, size_t need, size_t smem_optin, size_t* configured
     return BM25_OK;
 }
 
-template <int NCW>
-int launch_score_w(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int64_t grid, cudaStream_t st) {
-    static thread_local size_t configured[64] = {0};
-    int rc = configure_smem(k_score_topk<NCW>, lp.smem, ix->smem_optin, &configured[ix->device % 64]);
-    if (rc) return rc;
-    k_score_topk<NCW><<<(unsigned)grid, (NCW + 2) * 32, lp.smem, st>>>(a);
-    return BM25_OK;
-}
-
 int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int64_t Q, bool dense, cudaStream_t st) {
     const int64_t grid = Q * lp.splits;
     if (grid > 0x7fffffffLL) return fail(BM25_ERR_UNSUPPORTED, "grid too large");
@@ -347,13 +358,9 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
         if ((rc = configure_smem(k_scores_dense, lp.smem, ix->smem_optin, &configured[ix->device % 64]))) return rc;
         k_scores_dense<<<(unsigned)grid, kThreads, lp.smem, st>>>(a);
     } else {
-        switch (lp.warps) {
-            case 4: rc = launch_score_w<4>(ix, lp, a, grid, st); break;
-            case 8: rc = launch_score_w<8>(ix, lp, a, grid, st); break;
-            case 16: rc = launch_score_w<16>(ix, lp, a, grid, st); break;
-            default: return fail(BM25_ERR_INVALID, "consumer_warps must be 4, 8 or 16");
-        }
-        if (rc) return rc;
+        static thread_local size_t configured[64] = {0};
+        if ((rc = configure_smem(k_score_topk, lp.smem, ix->smem_optin, &configured[ix->device % 64]))) return rc;
+        k_score_topk<<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
     }
     ++g_launches;
     CU(cudaGetLastError());
@@ -363,11 +370,11 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
 int launch_segments(bm25_index* ix, const LaunchPlan& lp, const int32_t* d_queries, int64_t Q, int64_t T,
                     cudaStream_t st) {
     const int64_t n_qt = Q * T;
-    int rc = ix->ws_seg.reserve((size_t)n_qt * (lp.n_tiles + 1));
+    int rc = ix->ws_seg.reserve((size_t)n_qt * (lp.seg_rows + 1));
     if (rc) return rc;
     const int64_t blocks = (n_qt * 32 + 255) / 256;
     k_segments<<<(unsigned)blocks, 256, 0, st>>>(ix->d_indptr, ix->d_ids, d_queries, n_qt, (int)T, (int)ix->n_terms,
-                                                 lp.tile_docs, lp.n_tiles, ix->ws_seg.p);
+                                                 lp.seg_docs, lp.seg_rows, ix->ws_seg.p);
     ++g_launches;
     CU(cudaGetLastError());
     return BM25_OK;
@@ -398,9 +405,11 @@ int merge_P(int64_t total, int k_out) {
 int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T, int k, int32_t* d_out_ids,
                   float* d_out_scores, cudaStream_t st) {
     LaunchPlan lp;
-    int rc = make_plan(ix, Q, T, k, false, &lp);
+    int rc = make_plan(ix, Q, T, k, &lp);
     if (rc) return rc;
     if ((rc = ix->ws_partial.reserve((size_t)Q * lp.splits * k))) return rc;
+    if ((rc = ix->ws_theta.reserve((size_t)Q))) return rc;
+    CU(cudaMemsetAsync(ix->ws_theta.p, 0, (size_t)Q * sizeof(u64), st));
     const bool timing = ix->opt_timing != 0;
     if (timing) {
         for (auto& e : ix->ev)
@@ -416,6 +425,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.queries = d_queries;
     a.seg = ix->ws_seg.p;
     a.partial = ix->ws_partial.p;
+    a.theta_q = ix->opt_no_theta_share ? nullptr : ix->ws_theta.p;
     a.dense_out = nullptr;
     a.theta0 = lp.theta0;
     a.Q = (int)Q;
@@ -424,12 +434,11 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.n_docs = (int)ix->n_docs;
     a.tile_docs = lp.tile_docs;
     a.n_tiles = lp.n_tiles;
+    a.tiles_per_chunk = lp.tiles_per_chunk;
+    a.n_chunks = lp.n_chunks;
     a.splits = lp.splits;
-    a.tiles_per_split = lp.tiles_per_split;
+    a.tiles_per_split = 0;
     a.cap = lp.cap;
-    a.stage_postings = lp.stage;
-    a.n_stages = lp.stages;
-    a.sparse_max = lp.sparse_max;
     a.general = lp.general;
     if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
@@ -624,6 +633,7 @@ int bm25_index_destroy(bm25_index* ix) {
         }
         ix->ws_seg.release();
         ix->ws_partial.release();
+        ix->ws_theta.release();
         ix->ws_queries.release();
         ix->ws_out_ids.release();
         ix->ws_out_scores.release();
@@ -663,24 +673,17 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
     } else if (!strcmp(name, "splits")) {
         if (value < 0 || value > 65536) return fail(BM25_ERR_INVALID, "splits out of range");
         ix->opt_splits = (int)value;
-    } else if (!strcmp(name, "stage_postings")) {
-        if (value < 0 || value > (1 << 15)) return fail(BM25_ERR_INVALID, "stage_postings out of range");
-        ix->opt_stage = (int)value;
     } else if (!strcmp(name, "consumer_warps")) {
-        if (value != 0 && value != 4 && value != 8 && value != 16)
-            return fail(BM25_ERR_INVALID, "consumer_warps must be 0, 4, 8 or 16");
+        if (value < 0 || value > 16) return fail(BM25_ERR_INVALID, "consumer_warps must be 0..16");
         ix->opt_warps = (int)value;
-    } else if (!strcmp(name, "stages")) {
-        if (value != 0 && (value < 2 || value > kMaxStages)) return fail(BM25_ERR_INVALID, "stages must be 0 or 2..4");
-        ix->opt_stages = (int)value;
-    } else if (!strcmp(name, "sparse_pct")) {
-        if (value < 0 || value > 100) return fail(BM25_ERR_INVALID, "sparse_pct out of range");
-        ix->opt_sparse_pct = (int)value;
-    } else if (!strcmp(name, "sparse_off")) {
-        ix->opt_sparse_off = value ? 1 : 0;
     } else if (!strcmp(name, "cap")) {
         if (value < 0 || value > (1 << 14)) return fail(BM25_ERR_INVALID, "cap out of range");
         ix->opt_cap = (int)value;
+    } else if (!strcmp(name, "waves")) {
+        if (value < 0 || value > 64) return fail(BM25_ERR_INVALID, "waves out of range");
+        ix->opt_waves = (int)value;
+    } else if (!strcmp(name, "no_theta_share")) {
+        ix->opt_no_theta_share = value ? 1 : 0;
     } else if (!strcmp(name, "force_general")) {
         ix->opt_force_general = value ? 1 : 0;
     } else if (!strcmp(name, "timing")) {
@@ -755,7 +758,7 @@ int bm25_scores_dense(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64
     std::lock_guard<std::mutex> lock(ix->mu);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     LaunchPlan lp;
-    int rc = make_plan(ix, Q, T, 1, true, &lp);
+    int rc = make_plan_dense(ix, Q, T, &lp);
     if (rc) return rc;
     if ((rc = launch_segments(ix, lp, d_queries, Q, T, st))) return rc;
     SearchArgs a{};

@@ -6,11 +6,11 @@
 // and select the top-k by (score desc, doc id asc).
 //
 // Kernels:
-//   k_segments      per (query, term): posting-index boundaries of every document tile
+//   k_segments      per (query, term): posting-index boundaries of every document chunk
 //                   (binary search on doc id inside the term's posting slice)
-//   k_score_topk    one CTA per (query, tile range): shared-memory score tile, in-order
-//                   accumulation, fused threshold-pruned scan into a candidate buffer,
-//                   block-wide select; emits k sorted 64-bit keys per (query, range)
+//   k_score_topk    one warp per (query, document chunk): private shared-memory score tile,
+//                   in-order accumulation from per-term cursors, fused threshold-pruned scan
+//                   into the CTA's candidate buffer; emits k sorted 64-bit keys per (query, CTA)
 //   k_merge         per query: merge candidate lists (tile ranges or GPU shards), zero-score
 //                   fill, unpack to (doc id, score)
 //   k_validate_*    load-time canonical-form checks of the CSC arrays
@@ -143,16 +143,15 @@ struct SearchArgs {
     const int32_t* __restrict__ ids;      // [nnz]   doc ids, columns sorted ascending
     const float* __restrict__ w;          // [nnz]   weights
     const int32_t* __restrict__ queries;  // [Q,T]
-    const int32_t* __restrict__ seg;      // [Q,n_tiles+1,T]
+    const int32_t* __restrict__ seg;      // [Q,n_chunks+1,T]  (k_scores_dense: [Q,n_tiles+1,T])
     u64* __restrict__ partial;            // [Q,splits,k] sorted keys (0 = none)
+    u64* theta_q;                         // [Q] best known k-th key per query (shared by its CTAs)
     float* __restrict__ dense_out;        // [Q,n_docs]  (k_scores_dense only)
     u64 theta0;                           // initial threshold: key must be > theta0 to compete
     int Q, T, k;
-    int n_docs, tile_docs, n_tiles;
-    int splits, tiles_per_split, cap;
-    int stage_postings;                   // capacity of one staging buffer (multiple of 4)
-    int n_stages;                         // staging ring depth (2..4)
-    int sparse_max;                       // tiles with at most this many postings use the sparse epilogue
+    int n_docs, tile_docs, n_tiles;       // tile_docs = S, documents per warp tile
+    int tiles_per_chunk, n_chunks;        // a chunk = the tiles one warp walks
+    int splits, tiles_per_split, cap;     // splits = CTAs per query (tiles_per_split: k_scores_dense)
     int general;                          // 1: zero-score docs compete (weights may be <= 0)
 };
 
@@ -226,33 +225,28 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_score_topk (v3): the hot kernel.  CTA = (query, range of document tiles), warp-specialised,
-// no CTA-wide barrier on the steady-state path:
-//   producer warp : walks the tiles, packs the query terms' posting segments of a tile into
-//                   "rounds" that fit one staging buffer and issues them as 1-D bulk async copies
-//                   (TMA, UBLKCP) into an NS-stage shared-memory ring; completion on mbarriers.
-//   searcher warp : for every staged piece longer than kFilterMax postings, binary-searches (in
-//                   shared memory) the boundaries of the NCW document stripes of the tile, then
-//                   hands the stage to the consumers (second mbarrier).
-//   consumer warps: warp w OWNS stripe w of the score tile (tile_docs / NCW documents).  It adds
-//                   the postings of its stripe, piece by piece in query-term order (one fp32 add
-//                   per posting; a term has at most one posting per document and every posting of
-//                   a document is handled by the same warp, so __syncwarp between pieces is the
-//                   only ordering needed -- no atomics, no named barriers).  Epilogue per tile:
-//                     sparse tile (all postings resident in one stage, few of them): re-walk the
-//                       staged postings, test the final score against the running k-th best,
-//                       push survivors into the candidate buffer and zero the touched slots;
-//                     dense tile: vectorised scan + zero of the warp's stripe.
-//                   The candidate buffer is shared by the CTA; when it overflows the consumers
-//                   meet at a (rare) named-barrier round, keep the k best and raise the threshold.
+// k_score_topk (v4): the hot kernel.  Document-at-a-time streaming, one WARP per worker.
+//
+// CTA = (query, group of NCW document chunks); warp w of the CTA owns chunk sp*NCW + w, a
+// contiguous range of `tiles_per_chunk` document tiles of S = tile_docs documents, and a private
+// fp32 score tile of S slots in shared memory.  For every tile the warp walks the query's terms
+// strictly in query order; per term it keeps a cursor into the term's posting slice (the start
+// comes from the segment table, one entry per (query, chunk, term)) and pulls postings with
+// coalesced 128-byte loads -- 32 (narrow) or 128 (wide, for dense terms) at a time -- until the
+// first posting beyond the tile; each lane adds its in-tile postings into the score tile (one fp32
+// add per posting; a term has at most one posting per document and one warp handles every
+// posting of a document, so __syncwarp between terms is all the ordering needed: no atomics, no
+// CTA barriers, bit-identical to the reference's csc mat-vec).  A per-term "next doc id" lets the
+// warp skip terms with nothing in the tile without touching global memory.  After the last term
+// the warp scans + zeroes its tile with 16-byte vector accesses and pushes the documents that
+// beat the running k-th best key into the CTA's candidate buffer.  The buffer is shared by the
+// NCW warps; when it overflows they meet in a (rare) named-barrier round, keep the k best and
+// raise the threshold, which is also published per query in global memory so that the other
+// CTAs of the query prune with it.
 // shared memory (dynamic):
-//   float score[tile_docs] | int32 st_ids[NS][stg] | float st_w[NS][stg] | u64 cand[cap]
-//   | u64 full[4], ready[4], empty[4] | int rd[4][8] | int pc_so[NS][T] | int pc_cnt[NS][T]
-//   | int bnd[NS][T][NCW+1] | int p_lo[T], p_hi[T]
+//   float score[NCW][S] | u64 cand[cap] | int pos[NCW][T] | int cend[NCW][T] | int nxt[NCW][T]
 // ---------------------------------------------------------------------------------------------
-constexpr int kFilterMax = 64;   // pieces up to this many postings are filtered, not searched
-constexpr int kMaxStages = 4;
-constexpr int kFlagTileEnd = 1, kFlagSparse = 2;
+constexpr int kDocNone = 0x7fffffff;
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
@@ -279,14 +273,14 @@ struct TopkState {
     }
 };
 
-// vectorised scan + zero of one warp's stripe (S documents, the first nd_w of them real)
-__device__ __forceinline__ bool stripe_scan(float* scw, int S, int nd_w, uint32_t doc0, int lane, TopkState& tk) {
+// vectorised scan + zero of one warp's tile (S documents, the first nd_w of them real)
+__device__ __forceinline__ bool tile_scan(float* scw, int S, int nd_w, uint32_t doc0, int lane, TopkState& tk) {
     bool left = false;
 #pragma unroll 2
     for (int idx = lane * 4; idx < S; idx += 128) {
         const float4 v = *reinterpret_cast<const float4*>(scw + idx);
         float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (v.x >= tk.theta_f || v.y >= tk.theta_f || v.z >= tk.theta_f || v.w >= tk.theta_f) {
+        if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= tk.theta_f) {
             const float vv[4] = {v.x, v.y, v.z, v.w};
             float zz[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -302,24 +296,15 @@ __device__ __forceinline__ bool stripe_scan(float* scw, int S, int nd_w, uint32_
     return left;
 }
 
-template <int NCW>
-__global__ void __launch_bounds__((NCW + 2) * 32) k_score_topk(const SearchArgs a) {
-    constexpr int NC = NCW * 32;
+__global__ void __launch_bounds__(512) k_score_topk(const SearchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int T = a.T, stg = a.stage_postings, cap = a.cap, NS = a.n_stages;
+    const int NCW = blockDim.x >> 5;
+    const int T = a.T, S = a.tile_docs, cap = a.cap;
     float* sc = reinterpret_cast<float*>(smem_raw);
-    int32_t* st_ids = reinterpret_cast<int32_t*>(smem_raw + (size_t)a.tile_docs * 4);
-    float* st_w = reinterpret_cast<float*>(st_ids + NS * stg);
-    u64* cand = reinterpret_cast<u64*>(st_w + NS * stg);
-    u64* bar_full = cand + cap;
-    u64* bar_ready = bar_full + kMaxStages;
-    u64* bar_empty = bar_ready + kMaxStages;
-    int* rd = reinterpret_cast<int*>(bar_empty + kMaxStages);  // [4][8] = {n_pieces, base, nd, flags}
-    int* pc_so = rd + kMaxStages * 8;
-    int* pc_cnt = pc_so + NS * T;
-    int* bnd = pc_cnt + NS * T;
-    int* p_lo = bnd + NS * T * (NCW + 1);
-    int* p_hi = p_lo + T;
+    u64* cand = reinterpret_cast<u64*>(sc + (size_t)NCW * S);
+    int* st_pos = reinterpret_cast<int*>(cand + cap);
+    int* st_end = st_pos + NCW * T;
+    int* st_nxt = st_end + NCW * T;
     __shared__ int s_ncand, s_overflow;
     __shared__ u64 s_theta;
 
@@ -328,155 +313,40 @@ __global__ void __launch_bounds__((NCW + 2) * 32) k_score_topk(const SearchArgs 
     const int warp = tid >> 5;
     const int q = blockIdx.x / a.splits;
     const int sp = blockIdx.x - q * a.splits;
-    const int j0 = sp * a.tiles_per_split;
-    const int j1 = min(a.n_tiles, j0 + a.tiles_per_split);
-    const int S = a.tile_docs / NCW;  // documents per consumer stripe (multiple of 128)
+    const int chunk = sp * NCW + warp;
+    const ConsumerGroup grp{(int)blockDim.x, tid};
 
-    for (int i = tid * 4; i < a.tile_docs; i += (NC + 64) * 4)
-        *reinterpret_cast<float4*>(sc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    float* scw = sc + (size_t)warp * S;
+    for (int i = lane * 4; i < S; i += 128) *reinterpret_cast<float4*>(scw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
         s_ncand = 0;
         s_overflow = 0;
-        s_theta = a.theta0;
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(bar_full + s, 1);
-            mbar_init(bar_ready + s, 32);
-            mbar_init(bar_empty + s, NCW);
-        }
-        mbar_fence_init();
+        const u64 shared_theta = a.theta_q ? *reinterpret_cast<volatile u64*>(a.theta_q + q) : 0ull;
+        s_theta = shared_theta > a.theta0 ? shared_theta : a.theta0;
     }
     __syncthreads();
 
-    if (warp == NCW) {
-        // =============================== producer warp ========================================
-        const int32_t* segq = a.seg + (int64_t)q * (a.n_tiles + 1) * T;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int t = lane; t < T; t += 32) p_hi[t] = __ldg(segq + (int64_t)j0 * T + t);
-        for (int j = j0; j < j1; ++j) {
-            int tot = 0, npost = 0;
-            for (int t = lane; t < T; t += 32) {
-                const int lo = p_hi[t];
-                const int hi = __ldg(segq + (int64_t)(j + 1) * T + t);
-                p_lo[t] = lo;
-                p_hi[t] = hi;
-                if (hi > lo) {
-                    tot += ((hi + 3) & ~3) - (lo & ~3);
-                    npost += hi - lo;
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                tot += __shfl_xor_sync(kFull, tot, o);
-                npost += __shfl_xor_sync(kFull, npost, o);
-            }
-            __syncwarp();
-            if (npost == 0 && !a.general) continue;  // no posting of this query in the tile
-            int t = 0;
-            while (t < T && p_hi[t] <= p_lo[t]) ++t;
-            int pos = (t < T) ? p_lo[t] : 0;
-            const int base = j * a.tile_docs;
-            const int nd = min(a.tile_docs, a.n_docs - base);
-            // sparse epilogue only when the whole tile is resident in ONE round (tot + 8 <= stg guarantees it)
-            const int sparse = (!a.general && tot + 8 <= stg && npost <= a.sparse_max) ? kFlagSparse : 0;
-            do {  // one round = one staging buffer
-                mbar_wait(bar_empty + stage, phase ^ 1);
-                int used = 0, np = 0;
-                uint32_t bytes = 0;
-                while (t < T) {
-                    const int room = stg - used;
-                    if (room < 8) break;
-                    const int a0 = pos & ~3;
-                    const int skip = pos - a0;
-                    const int take = min(p_hi[t] - pos, room - skip);
-                    const int ncopy = ((pos + take + 3) & ~3) - a0;
-                    if (lane == 0) {
-                        pc_so[stage * T + np] = stage * stg + used + skip;
-                        pc_cnt[stage * T + np] = take;
-                        bulk_copy_g2s(st_ids + stage * stg + used, a.ids + a0, (uint32_t)ncopy * 4u, bar_full + stage);
-                        bulk_copy_g2s(st_w + stage * stg + used, a.w + a0, (uint32_t)ncopy * 4u, bar_full + stage);
-                    }
-                    bytes += (uint32_t)ncopy * 8u;
-                    used += ncopy;
-                    ++np;
-                    pos += take;
-                    if (pos < p_hi[t]) break;  // buffer full, the term continues in the next round
-                    ++t;
-                    while (t < T && p_hi[t] <= p_lo[t]) ++t;
-                    if (t < T) pos = p_lo[t];
-                }
-                if (lane == 0) {
-                    rd[stage * 8 + 0] = np;
-                    rd[stage * 8 + 1] = base;
-                    rd[stage * 8 + 2] = nd;
-                    rd[stage * 8 + 3] = ((t >= T) ? kFlagTileEnd : 0) | sparse;
-                    mbar_arrive_expect_tx(bar_full + stage, bytes);
-                }
-                __syncwarp();
-                if (++stage == NS) { stage = 0; phase ^= 1; }
-            } while (t < T);
-        }
-        mbar_wait(bar_empty + stage, phase ^ 1);
-        if (lane == 0) {
-            rd[stage * 8 + 0] = -1;  // end of stream
-            mbar_arrive(bar_full + stage);
-        }
-        return;
-    }
-
-    if (warp == NCW + 1) {
-        // =============================== searcher warp ========================================
-        int stage = 0;
-        uint32_t phase = 0;
-        for (;;) {
-            mbar_wait(bar_full + stage, phase);
-            const int np = rd[stage * 8 + 0];
-            if (np > 0) {
-                const int base = rd[stage * 8 + 1];
-                const int total = np * (NCW + 1);
-                for (int idx = lane; idx < total; idx += 32) {
-                    const int i = idx / (NCW + 1);
-                    const int b = idx - i * (NCW + 1);
-                    const int cnt = pc_cnt[stage * T + i];
-                    if (cnt <= kFilterMax) continue;
-                    const int so = pc_so[stage * T + i];
-                    int lo = 0, hi = cnt;
-                    if (b == 0) hi = 0;
-                    else if (b == NCW) lo = cnt;
-                    else {
-                        const int target = base + b * S;
-                        const int32_t* p = st_ids + so;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (p[mid] < target) lo = mid + 1; else hi = mid;
-                        }
-                    }
-                    bnd[(stage * T + i) * (NCW + 1) + b] = so + lo;
-                }
-            }
-            mbar_arrive(bar_ready + stage);  // all 32 lanes arrive (release of the bnd writes)
-            if (np < 0) return;
-            if (++stage == NS) { stage = 0; phase ^= 1; }
-        }
-    }
-
-    // ================================= consumer warps =========================================
-    const ConsumerGroup grp{NC, tid};
     TopkState tk{cand, &s_ncand, &s_overflow, cap, 0ull, 0.f};
-    tk.set_theta(a.theta0);
-    float* scw = sc + warp * S;
-    bool leftover = false;       // this warp's stripe still holds scores that did not fit in cand
+    tk.set_theta(s_theta);
+    bool leftover = false;       // this warp's tile still holds scores that did not fit in cand
     uint32_t left_doc0 = 0;
     int left_nd = 0;
 
-    // candidate-buffer overflow round: every consumer warp takes part (see the protocol above)
+    // candidate-buffer overflow round: every warp of the CTA takes part
     auto overflow_round = [&]() {
         for (;;) {
             compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
-            if (tid == 0) s_overflow = 0;
+            if (tid == 0) {
+                s_overflow = 0;
+                if (a.theta_q) {  // share the threshold with the other CTAs of this query
+                    const u64 mine = s_theta;
+                    const u64 old = atomicMax(a.theta_q + q, mine);
+                    if (old > mine) s_theta = old;
+                }
+            }
             grp.sync();
             tk.set_theta(s_theta);
-            if (leftover) leftover = __any_sync(kFull, stripe_scan(scw, S, left_nd, left_doc0, lane, tk));
+            if (leftover) leftover = __any_sync(kFull, tile_scan(scw, S, left_nd, left_doc0, lane, tk));
             grp.sync();
             const int again = ld_volatile(&s_overflow);
             grp.sync();
@@ -484,121 +354,113 @@ __global__ void __launch_bounds__((NCW + 2) * 32) k_score_topk(const SearchArgs 
         }
     };
 
-    int stage = 0;
-    uint32_t phase = 0;
-    for (;;) {
-        mbar_wait(bar_ready + stage, phase);
-        mbar_wait(bar_full + stage, phase);  // already complete; orders the bulk-copy writes for this thread
-        const int np = rd[stage * 8 + 0];
-        if (np < 0) break;
-        const int base = rd[stage * 8 + 1];
-        const int nd = rd[stage * 8 + 2];
-        const int flags = rd[stage * 8 + 3];
-        const int sbase = base + warp * S;  // first document of this warp's stripe
-        // ---- accumulate the round's pieces: terms strictly in query order ---------------------
-        for (int i = 0; i < np; ++i) {
-            const int cnt = pc_cnt[stage * T + i];
-            const int so = pc_so[stage * T + i];
-            if (cnt <= kFilterMax) {
-                for (int e = so + lane; e < so + cnt; e += 32) {
-                    const unsigned d = (unsigned)(st_ids[e] - sbase);
-                    if (d < (unsigned)S) scw[d] += st_w[e];
-                }
-            } else {
-                const int lo = bnd[(stage * T + i) * (NCW + 1) + warp];
-                const int hi = bnd[(stage * T + i) * (NCW + 1) + warp + 1];
-                for (int e = lo + lane; e < hi; e += 128) {
-                    const bool v1 = e + 32 < hi, v2 = e + 64 < hi, v3 = e + 96 < hi;
-                    const int i0 = st_ids[e] - sbase;
-                    const int i1 = v1 ? st_ids[e + 32] - sbase : 0;
-                    const int i2 = v2 ? st_ids[e + 64] - sbase : 0;
-                    const int i3 = v3 ? st_ids[e + 96] - sbase : 0;
-                    const float w0 = st_w[e];
-                    const float w1 = v1 ? st_w[e + 32] : 0.f;
-                    const float w2 = v2 ? st_w[e + 64] : 0.f;
-                    const float w3 = v3 ? st_w[e + 96] : 0.f;
-                    // one term has at most one posting per document: the four slots are distinct
-                    const float s0 = scw[i0];
-                    const float s1 = v1 ? scw[i1] : 0.f;
-                    const float s2 = v2 ? scw[i2] : 0.f;
-                    const float s3 = v3 ? scw[i3] : 0.f;
-                    scw[i0] = s0 + w0;
-                    if (v1) scw[i1] = s1 + w1;
-                    if (v2) scw[i2] = s2 + w2;
-                    if (v3) scw[i3] = s3 + w3;
-                }
-            }
-            __syncwarp();
+    if (chunk < a.n_chunks) {
+        int* pos_w = st_pos + warp * T;
+        int* end_w = st_end + warp * T;
+        int* nxt_w = st_nxt + warp * T;
+        const int32_t* seg0 = a.seg + ((int64_t)q * (a.n_chunks + 1) + chunk) * T;
+        for (int t = lane; t < T; t += 32) {
+            const int p = __ldg(seg0 + t), e = __ldg(seg0 + T + t);
+            pos_w[t] = p;
+            end_w[t] = e;
+            nxt_w[t] = (p < e) ? __ldg(a.ids + p) : kDocNone;
         }
-        bool left = false;
-        const bool sparse = (flags & (kFlagSparse | kFlagTileEnd)) == (kFlagSparse | kFlagTileEnd);
-        if (sparse) {
-            // ---- sparse epilogue: re-walk the staged postings, test + zero the touched slots ---
-            for (int i = 0; i < np; ++i) {
-                const int cnt = pc_cnt[stage * T + i];
-                const int so = pc_so[stage * T + i];
-                if (cnt <= kFilterMax) {
-                    for (int e = so + lane; e < so + cnt; e += 32) {
-                        const unsigned d = (unsigned)(st_ids[e] - sbase);
-                        if (d < (unsigned)S) {
-                            const float v = scw[d];
-                            if (v >= tk.theta_f && !tk.push(v, (uint32_t)sbase + d)) left = true;
-                            else scw[d] = 0.f;
+        __syncwarp();
+        const int j0 = chunk * a.tiles_per_chunk;
+        const int j1 = min(a.n_tiles, j0 + a.tiles_per_chunk);
+        for (int j = j0; j < j1; ++j) {
+            const int base = j * S;
+            const int tile_end = base + S;
+            bool touched = false;
+            // ---- accumulate: terms strictly in query order ------------------------------------
+            for (int t = 0; t < T; ++t) {
+                if (nxt_w[t] >= tile_end) continue;  // warp-uniform
+                touched = true;
+                int p = pos_w[t];
+                const int e = end_w[t];
+                int nx = kDocNone;
+                // dense term (>= 64 postings per remaining tile on average): 128 postings per step
+                if ((e - p) >= 64 * (j1 - j)) {
+                    for (;;) {
+                        const int r = e - p;  // > 0
+                        const int l0 = lane, l1 = lane + 32, l2 = lane + 64, l3 = lane + 96;
+                        const int d0 = l0 < r ? __ldg(a.ids + p + l0) : kDocNone;
+                        const int d1 = l1 < r ? __ldg(a.ids + p + l1) : kDocNone;
+                        const int d2 = l2 < r ? __ldg(a.ids + p + l2) : kDocNone;
+                        const int d3 = l3 < r ? __ldg(a.ids + p + l3) : kDocNone;
+                        const float w0 = l0 < r ? __ldg(a.w + p + l0) : 0.f;
+                        const float w1 = l1 < r ? __ldg(a.w + p + l1) : 0.f;
+                        const float w2 = l2 < r ? __ldg(a.w + p + l2) : 0.f;
+                        const float w3 = l3 < r ? __ldg(a.w + p + l3) : 0.f;
+                        const bool in0 = d0 < tile_end, in1 = d1 < tile_end, in2 = d2 < tile_end, in3 = d3 < tile_end;
+                        // one term has at most one posting per document: the four slots are distinct
+                        const float s0 = in0 ? scw[d0 - base] : 0.f;
+                        const float s1 = in1 ? scw[d1 - base] : 0.f;
+                        const float s2 = in2 ? scw[d2 - base] : 0.f;
+                        const float s3 = in3 ? scw[d3 - base] : 0.f;
+                        if (in0) scw[d0 - base] = s0 + w0;
+                        if (in1) scw[d1 - base] = s1 + w1;
+                        if (in2) scw[d2 - base] = s2 + w2;
+                        if (in3) scw[d3 - base] = s3 + w3;
+                        const unsigned b0 = __ballot_sync(kFull, in0), b1 = __ballot_sync(kFull, in1);
+                        const unsigned b2 = __ballot_sync(kFull, in2), b3 = __ballot_sync(kFull, in3);
+                        const int c = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+                        p += c;
+                        if (c < 128) {  // the first posting beyond the tile (if any) is element c
+                            const int dd = c < 32 ? d0 : (c < 64 ? d1 : (c < 96 ? d2 : d3));
+                            nx = __shfl_sync(kFull, dd, c & 31);
+                            break;
                         }
+                        if (p >= e) break;
                     }
                 } else {
-                    const int lo = bnd[(stage * T + i) * (NCW + 1) + warp];
-                    const int hi = bnd[(stage * T + i) * (NCW + 1) + warp + 1];
-                    for (int e = lo + lane; e < hi; e += 128) {
-                        const bool v1 = e + 32 < hi, v2 = e + 64 < hi, v3 = e + 96 < hi;
-                        const int i0 = st_ids[e] - sbase;
-                        const int i1 = v1 ? st_ids[e + 32] - sbase : i0;
-                        const int i2 = v2 ? st_ids[e + 64] - sbase : i0;
-                        const int i3 = v3 ? st_ids[e + 96] - sbase : i0;
-                        const float s0 = scw[i0], s1 = scw[i1], s2 = scw[i2], s3 = scw[i3];
-                        bool k0 = false, k1 = false, k2 = false, k3 = false;  // keep (buffer full)
-                        if (s0 >= tk.theta_f) k0 = !tk.push(s0, (uint32_t)(sbase + i0));
-                        if (v1 && s1 >= tk.theta_f) k1 = !tk.push(s1, (uint32_t)(sbase + i1));
-                        if (v2 && s2 >= tk.theta_f) k2 = !tk.push(s2, (uint32_t)(sbase + i2));
-                        if (v3 && s3 >= tk.theta_f) k3 = !tk.push(s3, (uint32_t)(sbase + i3));
-                        if (!k0) scw[i0] = 0.f;
-                        if (v1 && !k1) scw[i1] = 0.f;
-                        if (v2 && !k2) scw[i2] = 0.f;
-                        if (v3 && !k3) scw[i3] = 0.f;
-                        left |= k0 | k1 | k2 | k3;
+                    for (;;) {
+                        const int r = e - p;  // > 0
+                        const int d = lane < r ? __ldg(a.ids + p + lane) : kDocNone;
+                        const float w = lane < r ? __ldg(a.w + p + lane) : 0.f;
+                        const bool in = d < tile_end;
+                        if (in) scw[d - base] += w;
+                        const int c = __popc(__ballot_sync(kFull, in));
+                        p += c;
+                        if (c < 32) {
+                            nx = __shfl_sync(kFull, d, c);
+                            break;
+                        }
+                        if (p >= e) break;
                     }
+                }
+                if (lane == 0) {
+                    pos_w[t] = p;
+                    nxt_w[t] = nx;
                 }
                 __syncwarp();
             }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + stage);  // staging buffer may be refilled
-        if (++stage == NS) { stage = 0; phase ^= 1; }
-        if (flags & kFlagTileEnd) {
-            const int nd_w = min(max(nd - warp * S, 0), S);
-            if (!sparse) left = stripe_scan(scw, S, nd_w, (uint32_t)sbase, lane, tk);
-            if (__any_sync(kFull, left)) {
-                leftover = true;
-                left_doc0 = (uint32_t)sbase;
-                left_nd = nd_w;
+            // ---- scan + zero the tile, push the documents that beat the k-th best so far ------
+            if (touched || a.general) {
+                const int nd_w = min(S, a.n_docs - base);
+                const bool left = tile_scan(scw, S, nd_w, (uint32_t)base, lane, tk);
+                if (__any_sync(kFull, left)) {
+                    leftover = true;
+                    left_doc0 = (uint32_t)base;
+                    left_nd = nd_w;
+                }
+            }
+            if (leftover || ld_volatile(&s_overflow)) {
+                grp.sync();
+                overflow_round();
             }
         }
-        // checked after EVERY round (not only at tile ends): a warp that is ahead in the ring must be
-        // able to join the barrier without waiting for a stage the blocked warps have not released
-        if (leftover || ld_volatile(&s_overflow)) {
-            grp.sync();
-            overflow_round();
-        }
     }
-    for (;;) {  // finished: keep serving overflow rounds until every consumer warp is here
+    for (;;) {  // finished: keep serving overflow rounds until every warp of the CTA is here
         grp.sync();
         if (!ld_volatile(&s_overflow)) break;
         overflow_round();
     }
     compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
+    if (tid == 0 && a.theta_q && s_ncand >= a.k) atomicMax(a.theta_q + q, s_theta);
     const int n = s_ncand;
     u64* out = a.partial + ((int64_t)q * a.splits + sp) * a.k;
-    for (int i = tid; i < a.k; i += NC) out[i] = (i < n) ? cand[i] : 0ull;
+    for (int i = tid; i < a.k; i += blockDim.x) out[i] = (i < n) ? cand[i] : 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ from mojo_bm25_b200 import engine, synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--workloads", default="B")
 ap.add_argument("--configs", default="default", help="comma list of option sets, each 'name=value:name=value' "
-                "(bm25_index_set_option names: tile_docs, splits, consumer_warps, stage_postings, stages, cap, sparse_pct, sparse_off)")
+                "(bm25_index_set_option names: tile_docs, splits, consumer_warps, cap, waves, no_theta_share)")
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--scale", type=float, default=1.0)
 args = ap.parse_args()
@@ -28,7 +28,7 @@ for wl in args.workloads.split(","):
     print(f"# {wl}: docs={idx.n_docs} terms={idx.n_terms} nnz={idx.nnz} Q={q.shape[0]} T={q.shape[1]} k={k} "
           f"posting_bytes={pbytes/1e9:.3f} GB", flush=True)
     for cfg in args.configs.split(","):
-        opts = dict(tile_docs=0, splits=0, consumer_warps=0, stage_postings=0, stages=0, cap=0, sparse_pct=0, sparse_off=0)
+        opts = dict(tile_docs=0, splits=0, consumer_warps=0, cap=0, waves=0, no_theta_share=0)
         if cfg != "default":
             for kv in cfg.split(":"):
                 name, val = kv.split("=")
