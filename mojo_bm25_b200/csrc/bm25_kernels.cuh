@@ -273,10 +273,43 @@ struct TopkState {
     }
 };
 
+// 128 consecutive postings of one term, four per lane (lane, lane+32, lane+64, lane+96)
+struct PostingChunk {
+    int d0, d1, d2, d3;
+    float w0, w1, w2, w3;
+    __device__ __forceinline__ void load(const int32_t* __restrict__ ids, const float* __restrict__ w, int p, int r, int lane) {
+        const int l0 = lane, l1 = lane + 32, l2 = lane + 64, l3 = lane + 96;
+        d0 = l0 < r ? __ldg(ids + p + l0) : kDocNone;
+        d1 = l1 < r ? __ldg(ids + p + l1) : kDocNone;
+        d2 = l2 < r ? __ldg(ids + p + l2) : kDocNone;
+        d3 = l3 < r ? __ldg(ids + p + l3) : kDocNone;
+        w0 = l0 < r ? __ldg(w + p + l0) : 0.f;
+        w1 = l1 < r ? __ldg(w + p + l1) : 0.f;
+        w2 = l2 < r ? __ldg(w + p + l2) : 0.f;
+        w3 = l3 < r ? __ldg(w + p + l3) : 0.f;
+    }
+    __device__ __forceinline__ int doc(int i) const { return i == 0 ? d0 : (i == 1 ? d1 : (i == 2 ? d2 : d3)); }
+    // adds the postings with doc < tile_end into the tile; returns how many (a prefix: ids ascend)
+    __device__ __forceinline__ int add_into(float* scw, int base, int tile_end) const {
+        const bool in0 = d0 < tile_end, in1 = d1 < tile_end, in2 = d2 < tile_end, in3 = d3 < tile_end;
+        // one term has at most one posting per document: the four slots are distinct
+        const float s0 = in0 ? scw[d0 - base] : 0.f;
+        const float s1 = in1 ? scw[d1 - base] : 0.f;
+        const float s2 = in2 ? scw[d2 - base] : 0.f;
+        const float s3 = in3 ? scw[d3 - base] : 0.f;
+        if (in0) scw[d0 - base] = s0 + w0;
+        if (in1) scw[d1 - base] = s1 + w1;
+        if (in2) scw[d2 - base] = s2 + w2;
+        if (in3) scw[d3 - base] = s3 + w3;
+        return __popc(__ballot_sync(kFull, in0)) + __popc(__ballot_sync(kFull, in1)) +
+               __popc(__ballot_sync(kFull, in2)) + __popc(__ballot_sync(kFull, in3));
+    }
+};
+
 // vectorised scan + zero of one warp's tile (S documents, the first nd_w of them real)
 __device__ __forceinline__ bool tile_scan(float* scw, int S, int nd_w, uint32_t doc0, int lane, TopkState& tk) {
     bool left = false;
-#pragma unroll 2
+#pragma unroll 4
     for (int idx = lane * 4; idx < S; idx += 128) {
         const float4 v = *reinterpret_cast<const float4*>(scw + idx);
         float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -373,67 +406,86 @@ __global__ void __launch_bounds__(512) k_score_topk(const SearchArgs a) {
             const int tile_end = base + S;
             bool touched = false;
             // ---- accumulate: terms strictly in query order ------------------------------------
-            for (int t = 0; t < T; ++t) {
-                if (nxt_w[t] >= tile_end) continue;  // warp-uniform
-                touched = true;
-                int p = pos_w[t];
-                const int e = end_w[t];
-                int nx = kDocNone;
-                // dense term (>= 64 postings per remaining tile on average): 128 postings per step
-                if ((e - p) >= 64 * (j1 - j)) {
-                    for (;;) {
-                        const int r = e - p;  // > 0
-                        const int l0 = lane, l1 = lane + 32, l2 = lane + 64, l3 = lane + 96;
-                        const int d0 = l0 < r ? __ldg(a.ids + p + l0) : kDocNone;
-                        const int d1 = l1 < r ? __ldg(a.ids + p + l1) : kDocNone;
-                        const int d2 = l2 < r ? __ldg(a.ids + p + l2) : kDocNone;
-                        const int d3 = l3 < r ? __ldg(a.ids + p + l3) : kDocNone;
-                        const float w0 = l0 < r ? __ldg(a.w + p + l0) : 0.f;
-                        const float w1 = l1 < r ? __ldg(a.w + p + l1) : 0.f;
-                        const float w2 = l2 < r ? __ldg(a.w + p + l2) : 0.f;
-                        const float w3 = l3 < r ? __ldg(a.w + p + l3) : 0.f;
-                        const bool in0 = d0 < tile_end, in1 = d1 < tile_end, in2 = d2 < tile_end, in3 = d3 < tile_end;
-                        // one term has at most one posting per document: the four slots are distinct
-                        const float s0 = in0 ? scw[d0 - base] : 0.f;
-                        const float s1 = in1 ? scw[d1 - base] : 0.f;
-                        const float s2 = in2 ? scw[d2 - base] : 0.f;
-                        const float s3 = in3 ? scw[d3 - base] : 0.f;
-                        if (in0) scw[d0 - base] = s0 + w0;
-                        if (in1) scw[d1 - base] = s1 + w1;
-                        if (in2) scw[d2 - base] = s2 + w2;
-                        if (in3) scw[d3 - base] = s3 + w3;
-                        const unsigned b0 = __ballot_sync(kFull, in0), b1 = __ballot_sync(kFull, in1);
-                        const unsigned b2 = __ballot_sync(kFull, in2), b3 = __ballot_sync(kFull, in3);
-                        const int c = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
-                        p += c;
-                        if (c < 128) {  // the first posting beyond the tile (if any) is element c
-                            const int dd = c < 32 ? d0 : (c < 64 ? d1 : (c < 96 ? d2 : d3));
-                            nx = __shfl_sync(kFull, dd, c & 31);
-                            break;
+            // The terms with a posting in this tile are taken four at a time: the first 32
+            // postings of each are requested together (memory-level parallelism across terms),
+            // then added one term after the other.
+            for (int g0 = 0; g0 < T; g0 += 32) {
+                const int tl = g0 + lane;
+                unsigned act = __ballot_sync(kFull, tl < T && nxt_w[min(tl, T - 1)] < tile_end);
+                if (act) touched = true;
+                while (act) {
+                    int tt[4], pp[4], ee[4], dd[4];
+                    float ww[4];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        tt[g] = -1;
+                        if (act) {
+                            const int t = g0 + __ffs(act) - 1;
+                            act &= act - 1;
+                            tt[g] = t;
+                            pp[g] = pos_w[t];
+                            ee[g] = end_w[t];
+                            const int r = ee[g] - pp[g];
+                            dd[g] = lane < r ? __ldg(a.ids + pp[g] + lane) : kDocNone;
+                            ww[g] = lane < r ? __ldg(a.w + pp[g] + lane) : 0.f;
                         }
-                        if (p >= e) break;
                     }
-                } else {
-                    for (;;) {
-                        const int r = e - p;  // > 0
-                        const int d = lane < r ? __ldg(a.ids + p + lane) : kDocNone;
-                        const float w = lane < r ? __ldg(a.w + p + lane) : 0.f;
-                        const bool in = d < tile_end;
-                        if (in) scw[d - base] += w;
-                        const int c = __popc(__ballot_sync(kFull, in));
-                        p += c;
-                        if (c < 32) {
-                            nx = __shfl_sync(kFull, d, c);
-                            break;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        if (tt[g] < 0) break;  // warp-uniform
+                        int p = pp[g];
+                        const int e = ee[g];
+                        int nx = kDocNone;
+                        {
+                            const bool in = dd[g] < tile_end;
+                            if (in) scw[dd[g] - base] += ww[g];
+                            const int c = __popc(__ballot_sync(kFull, in));
+                            p += c;
+                            if (c < 32) nx = __shfl_sync(kFull, dd[g], c);
+                            else if (p < e) nx = -1;  // more of this term may lie in the tile
                         }
-                        if (p >= e) break;
+                        if (nx == -1) {
+                            nx = kDocNone;
+                            if ((e - p) >= 64 * (j1 - j)) {
+                                // dense term (>= 64 postings per remaining tile on average): 128
+                                // postings per step, the next step's loads already in flight
+                                PostingChunk A, B;
+                                A.load(a.ids, a.w, p, e - p, lane);
+                                for (;;) {
+                                    B.load(a.ids, a.w, p + 128, e - p - 128, lane);
+                                    const int c = A.add_into(scw, base, tile_end);
+                                    p += c;
+                                    if (c < 128) {  // the first posting beyond the tile (if any) is element c
+                                        nx = __shfl_sync(kFull, A.doc(c >> 5), c & 31);
+                                        break;
+                                    }
+                                    if (p >= e) break;
+                                    A = B;
+                                }
+                            } else {
+                                for (;;) {
+                                    const int r = e - p;  // > 0
+                                    const int d = lane < r ? __ldg(a.ids + p + lane) : kDocNone;
+                                    const float w = lane < r ? __ldg(a.w + p + lane) : 0.f;
+                                    const bool in = d < tile_end;
+                                    if (in) scw[d - base] += w;
+                                    const int c = __popc(__ballot_sync(kFull, in));
+                                    p += c;
+                                    if (c < 32) {
+                                        nx = __shfl_sync(kFull, d, c);
+                                        break;
+                                    }
+                                    if (p >= e) break;
+                                }
+                            }
+                        }
+                        if (lane == 0) {
+                            pos_w[tt[g]] = p;
+                            nxt_w[tt[g]] = nx;
+                        }
+                        __syncwarp();
                     }
                 }
-                if (lane == 0) {
-                    pos_w[t] = p;
-                    nxt_w[t] = nx;
-                }
-                __syncwarp();
             }
             // ---- scan + zero the tile, push the documents that beat the k-th best so far ------
             if (touched || a.general) {
