@@ -155,10 +155,11 @@ struct bm25_index {
     int32_t* d_indptr = nullptr;
     int32_t* d_ids = nullptr;
     float* d_w = nullptr;
+    float* d_bounds = nullptr;  // [n_terms][kBoundLevels] per-term weight order statistics (threshold priming)
     std::vector<int32_t> h_indptr;  // host copy for byte accounting / validation
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
-    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0;
+    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace
@@ -183,6 +184,7 @@ struct bm25_index {
     int64_t device_bytes() const {
         int64_t b = 0;
         if (!borrowed) b += (n_terms + 1) * 4 + nnz * 8;
+        if (d_bounds) b += n_terms * kBoundLevels * 4;
         b += ws_seg.bytes() + ws_partial.bytes() + ws_theta.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
              ws_out_scores.bytes();
         return b;
@@ -196,6 +198,17 @@ int finish_create(bm25_index* ix, const cudaDeviceProp& prop) {
     ix->smem_optin = prop.sharedMemPerBlockOptin;
     ix->smem_per_sm = prop.sharedMemPerMultiprocessor;
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
+    if (ix->all_positive && ix->n_terms > 0 && ix->nnz > 0) {
+        // threshold priming table (see k_term_bounds / k_segments)
+        if (cudaMalloc(&ix->d_bounds, (size_t)ix->n_terms * kBoundLevels * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(BM25_ERR_OOM, "cudaMalloc of the term-bound table failed");
+        }
+        k_term_bounds<<<(unsigned)ix->n_terms, 128>>>(ix->d_indptr, ix->d_w, (int)ix->n_terms, ix->d_bounds);
+        ++g_launches;
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+    }
     return BM25_OK;
 }
 
@@ -305,6 +318,11 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
     *lp = LaunchPlan{};
     lp->warps = ix->warps();
     lp->tile_docs = ix->tile_docs();
+    // long queries are bound by per-(tile, term) latency: more, smaller warp tiles per SM
+    if (T >= 32 && ix->opt_warps == 0 && ix->opt_tile_docs == 0 && ix->n_docs >= 16 * 1024) {
+        lp->warps = 16;
+        lp->tile_docs = 1024;
+    }
     lp->cap = ix->opt_cap > 0 ? next_pow2(ix->opt_cap) : next_pow2(std::max(2 * (int64_t)k, (int64_t)512));
     if (lp->cap < k + 64) lp->cap = next_pow2((int64_t)k + 64);
     // shrink the CTA (fewer warps, then smaller tiles) until it fits into shared memory
@@ -367,14 +385,19 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
     return BM25_OK;
 }
 
-int launch_segments(bm25_index* ix, const LaunchPlan& lp, const int32_t* d_queries, int64_t Q, int64_t T,
-                    cudaStream_t st) {
+int launch_segments(bm25_index* ix, const LaunchPlan& lp, const int32_t* d_queries, int64_t Q, int64_t T, int k,
+                    u64* theta_q, cudaStream_t st) {
     const int64_t n_qt = Q * T;
     int rc = ix->ws_seg.reserve((size_t)n_qt * (lp.seg_rows + 1));
     if (rc) return rc;
+    // threshold priming needs positive weights, a shared per-query threshold and k <= 2^(levels-1)
+    int level = 0;
+    while ((1 << level) < k) ++level;
+    const bool prime = theta_q && ix->d_bounds && !lp.general && level < kBoundLevels && !ix->opt_no_priming;
     const int64_t blocks = (n_qt * 32 + 255) / 256;
     k_segments<<<(unsigned)blocks, 256, 0, st>>>(ix->d_indptr, ix->d_ids, d_queries, n_qt, (int)T, (int)ix->n_terms,
-                                                 lp.seg_docs, lp.seg_rows, ix->ws_seg.p);
+                                                 lp.seg_docs, lp.seg_rows, ix->ws_seg.p,
+                                                 prime ? ix->d_bounds : nullptr, level, theta_q);
     ++g_launches;
     CU(cudaGetLastError());
     return BM25_OK;
@@ -417,7 +440,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
         ix->ev_valid = false;
         CU(cudaEventRecord(ix->ev[0], st));
     }
-    if ((rc = launch_segments(ix, lp, d_queries, Q, T, st))) return rc;
+    if ((rc = launch_segments(ix, lp, d_queries, Q, T, k, ix->opt_no_theta_share ? nullptr : ix->ws_theta.p, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[1], st));
     SearchArgs a{};
     a.ids = ix->d_ids;
@@ -631,6 +654,7 @@ int bm25_index_destroy(bm25_index* ix) {
             if (ix->d_ids) cudaFree(ix->d_ids);
             if (ix->d_w) cudaFree(ix->d_w);
         }
+        if (ix->d_bounds) cudaFree(ix->d_bounds);
         ix->ws_seg.release();
         ix->ws_partial.release();
         ix->ws_theta.release();
@@ -684,6 +708,8 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
         ix->opt_waves = (int)value;
     } else if (!strcmp(name, "no_theta_share")) {
         ix->opt_no_theta_share = value ? 1 : 0;
+    } else if (!strcmp(name, "no_priming")) {
+        ix->opt_no_priming = value ? 1 : 0;
     } else if (!strcmp(name, "force_general")) {
         ix->opt_force_general = value ? 1 : 0;
     } else if (!strcmp(name, "timing")) {
@@ -760,7 +786,7 @@ int bm25_scores_dense(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64
     LaunchPlan lp;
     int rc = make_plan_dense(ix, Q, T, &lp);
     if (rc) return rc;
-    if ((rc = launch_segments(ix, lp, d_queries, Q, T, st))) return rc;
+    if ((rc = launch_segments(ix, lp, d_queries, Q, T, 1, nullptr, st))) return rc;
     SearchArgs a{};
     a.ids = ix->d_ids;
     a.w = ix->d_w;

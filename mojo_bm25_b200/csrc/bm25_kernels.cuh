@@ -26,6 +26,8 @@ typedef unsigned long long u64;
 constexpr int kThreads = 512;          // threads per CTA of k_score_topk / k_merge
 constexpr int kChunk = kThreads * 4;   // documents scanned per block-wide step (float4 / thread)
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kBoundLevels = 11;       // per-term weight order statistics at ranks 1, 2, 4, ..., 1024
+constexpr int kBoundSample = 1024;     // postings sampled per term for those statistics
 
 // ---------------------------------------------------------------------------------------------
 // 64-bit candidate keys: high word = order-preserving image of the fp32 score, low word =
@@ -63,7 +65,9 @@ __global__ void __launch_bounds__(256) k_segments(const int32_t* __restrict__ in
                                                   const int32_t* __restrict__ ids,
                                                   const int32_t* __restrict__ queries, int64_t n_qt,
                                                   int T, int n_terms, int tile_docs, int n_tiles,
-                                                  int32_t* __restrict__ seg) {
+                                                  int32_t* __restrict__ seg,
+                                                  const float* __restrict__ bounds, int level,
+                                                  u64* __restrict__ theta_q) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp >= n_qt) return;
@@ -72,6 +76,13 @@ __global__ void __launch_bounds__(256) k_segments(const int32_t* __restrict__ in
     const int t = (int)(warp - q * T);
     int lo0 = 0, hi0 = 0;
     if (term >= 0 && term < n_terms) { lo0 = indptr[term]; hi0 = indptr[term + 1]; }
+    // threshold priming: the 2^level-th largest weight of this term belongs to 2^level distinct
+    // documents whose score is at least that weight (all weights > 0), so it bounds the k-th best
+    // score of the query from below for every k <= 2^level.
+    if (lane == 0 && bounds != nullptr && hi0 > lo0) {
+        const float b = __ldg(bounds + (int64_t)term * kBoundLevels + level);
+        if (b > 0.f) atomicMax(theta_q + q, make_key(b, 0xffffffffu) - 1ull);
+    }
     int32_t* out = seg + q * (int64_t)(n_tiles + 1) * T + t;
     for (int j = lane; j <= n_tiles; j += 32) {
         int res;
@@ -104,21 +115,37 @@ struct ConsumerGroup {
     }
 };
 
-// group-wide bitonic sort (descending) of P = 2^m keys in shared memory
+// group-wide bitonic sort (descending) of P = 2^m keys in shared memory.  A power-of-two number of
+// warps each own a contiguous slice of >= 64 keys: every stage whose compare distance stays inside
+// a slice needs only __syncwarp, so a sort of 512 keys by 8 warps meets at ~8 group barriers
+// instead of 45.
 template <typename G>
 __device__ __forceinline__ void bitonic_sort_desc(u64* buf, int P, const G& g) {
+    const int lane = g.rank & 31, warp = g.rank >> 5;
+    const int nw = g.size >> 5;
+    int nwu = 1;
+    while (nwu * 2 <= nw && P / (nwu * 2) >= 64) nwu <<= 1;
+    const int slice = P / nwu;  // keys per participating warp
+    const int half = slice >> 1;
+    bool prev_global = true;
     for (int size = 2; size <= P; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = g.rank; i < (P >> 1); i += g.size) {
-                const int a = 2 * i - (i & (stride - 1));
-                const int b = a + stride;
-                const bool desc = ((a & size) == 0);
-                const u64 x = buf[a], y = buf[b];
-                if ((x < y) == desc) { buf[a] = y; buf[b] = x; }
+            const bool global = stride >= slice;
+            if (global || prev_global) g.sync(); else __syncwarp();
+            prev_global = global;
+            if (warp < nwu) {
+                for (int m = lane; m < half; m += 32) {
+                    const int i = warp * half + m;
+                    const int a = 2 * i - (i & (stride - 1));
+                    const int b = a + stride;
+                    const bool desc = ((a & size) == 0);
+                    const u64 x = buf[a], y = buf[b];
+                    if ((x < y) == desc) { buf[a] = y; buf[b] = x; }
+                }
             }
-            g.sync();
         }
     }
+    g.sync();
 }
 
 // Keep the k best of the n = min(*s_ncand, cap) candidates (sorted, best first) and raise the
@@ -597,6 +624,34 @@ __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
                 ++pos;
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_term_bounds (load time): bounds[t][l] = the 2^l-th largest weight among the first
+// min(df_t, kBoundSample) postings of term t, or 0 when the term has fewer postings.  One CTA of
+// 128 threads per term; the sample is sorted in shared memory (as order-preserving keys).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_term_bounds(const int32_t* __restrict__ indptr, const float* __restrict__ w,
+                                                     int n_terms, float* __restrict__ bounds) {
+    __shared__ u64 buf[kBoundSample];
+    const int t = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lo = indptr[t];
+    const int m = min(indptr[t + 1] - lo, kBoundSample);
+    float* out = bounds + (int64_t)t * kBoundLevels;
+    if (m < 1) {
+        if (tid < kBoundLevels) out[tid] = 0.f;
+        return;
+    }
+    int P = 2;
+    while (P < m) P <<= 1;
+    for (int i = tid; i < P; i += 128) buf[i] = i < m ? ((u64)f32_to_ord(w[lo + i]) << 32) : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(buf, P, CtaGroup{128, tid});
+    if (tid < kBoundLevels) {
+        const int r = 1 << tid;
+        out[tid] = r <= m ? ord_to_f32((uint32_t)(buf[r - 1] >> 32)) : 0.f;
     }
 }
 
