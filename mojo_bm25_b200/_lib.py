@@ -44,6 +44,9 @@ def load(rebuild_if_stale: bool = True):
     if _lib is not None:
         return _lib
     so = _build.SO
+    alt = os.environ.get("BM25_B200_LIB")  # developer A/B switch: another build of the same C ABI
+    if alt:
+        so, rebuild_if_stale = alt, False
     if rebuild_if_stale and (not os.path.exists(so) or (_build.is_stale() and os.path.exists(_build.nvcc_path()))):
         so = _build.build()
     if not os.path.exists(so):
