@@ -159,7 +159,7 @@ struct bm25_index {
     std::vector<int32_t> h_indptr;  // host copy for byte accounting / validation
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
-    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0;
+    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace
@@ -280,7 +280,7 @@ struct LaunchPlan {
 
 // dynamic shared memory of k_score_topk (layout documented at the kernel)
 size_t score_smem(int tile_docs, int cap, int64_t T, int warps) {
-    return (size_t)warps * tile_docs * 4 + (size_t)cap * 8 + (size_t)warps * T * 12 + 128;
+    return (size_t)warps * tile_docs * 4 + (size_t)cap * 8 + (size_t)warps * T * 12 + (size_t)warps * kHotCap * 2 + 128;
 }
 
 void plan_mode(const bm25_index* ix, LaunchPlan* lp) {
@@ -376,9 +376,14 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
         if ((rc = configure_smem(k_scores_dense, lp.smem, ix->smem_optin, &configured[ix->device % 64]))) return rc;
         k_scores_dense<<<(unsigned)grid, kThreads, lp.smem, st>>>(a);
     } else {
-        static thread_local size_t configured[64] = {0};
-        if ((rc = configure_smem(k_score_topk, lp.smem, ix->smem_optin, &configured[ix->device % 64]))) return rc;
-        k_score_topk<<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
+        static thread_local size_t configured[2][64] = {{0}, {0}};
+        if (lp.warps <= 8) {
+            if ((rc = configure_smem(k_score_topk<256>, lp.smem, ix->smem_optin, &configured[0][ix->device % 64]))) return rc;
+            k_score_topk<256><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
+        } else {
+            if ((rc = configure_smem(k_score_topk<512>, lp.smem, ix->smem_optin, &configured[1][ix->device % 64]))) return rc;
+            k_score_topk<512><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
+        }
     }
     ++g_launches;
     CU(cudaGetLastError());
@@ -463,6 +468,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.tiles_per_split = 0;
     a.cap = lp.cap;
     a.general = lp.general;
+    a.no_hot = ix->opt_no_hot;
     if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
     MergeArgs m{};
@@ -710,6 +716,8 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
         ix->opt_no_theta_share = value ? 1 : 0;
     } else if (!strcmp(name, "no_priming")) {
         ix->opt_no_priming = value ? 1 : 0;
+    } else if (!strcmp(name, "no_hot")) {
+        ix->opt_no_hot = value ? 1 : 0;
     } else if (!strcmp(name, "force_general")) {
         ix->opt_force_general = value ? 1 : 0;
     } else if (!strcmp(name, "timing")) {

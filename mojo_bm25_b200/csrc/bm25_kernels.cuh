@@ -180,6 +180,7 @@ struct SearchArgs {
     int tiles_per_chunk, n_chunks;        // a chunk = the tiles one warp walks
     int splits, tiles_per_split, cap;     // splits = CTAs per query (tiles_per_split: k_scores_dense)
     int general;                          // 1: zero-score docs compete (weights may be <= 0)
+    int no_hot;                           // 1: always use the dense tile scan (A/B switch)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -265,13 +266,16 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
 // posting of a document, so __syncwarp between terms is all the ordering needed: no atomics, no
 // CTA barriers, bit-identical to the reference's csc mat-vec).  A per-term "next doc id" lets the
 // warp skip terms with nothing in the tile without touching global memory.  After the last term
-// the warp scans + zeroes its tile with 16-byte vector accesses and pushes the documents that
-// beat the running k-th best key into the CTA's candidate buffer.  The buffer is shared by the
+// the warp pushes the documents that beat the running k-th best key into the CTA's candidate
+// buffer -- from the short list of slots whose running score reached the threshold during the
+// adds, followed by a write-only clear of the tile, or (list overflow / non-positive weights) by a
+// 16-byte vector scan + zero of all S slots.  The buffer is shared by the
 // NCW warps; when it overflows they meet in a (rare) named-barrier round, keep the k best and
 // raise the threshold, which is also published per query in global memory so that the other
 // CTAs of the query prune with it.
 // shared memory (dynamic):
 //   float score[NCW][S] | u64 cand[cap] | int pos[NCW][T] | int cend[NCW][T] | int nxt[NCW][T]
+//   | uint16 hot[NCW][kHotCap]
 // ---------------------------------------------------------------------------------------------
 constexpr int kDocNone = 0x7fffffff;
 
@@ -300,6 +304,31 @@ struct TopkState {
     }
 };
 
+// Per-warp list of the tile slots whose running score reached the pre-filter threshold while
+// postings were being added ("hot" documents; weights are > 0 on this path so scores only grow and
+// every document that ends above the threshold is recorded, possibly more than once).  While the
+// list fits, the tile epilogue visits only these slots and then clears the tile with plain
+// 16-byte stores instead of reading and testing all S scores.
+constexpr int kHotCap = 64;
+struct HotList {
+    unsigned short* slots;  // [kHotCap] tile-local ids
+    int n;                  // warp-uniform; > kHotCap = overflowed or disabled -> dense scan
+    unsigned lt;            // lanemask_lt
+    __device__ __forceinline__ void reset(bool enabled) { n = enabled ? 0 : kHotCap + 1; }
+    __device__ __forceinline__ bool active() const { return n <= kHotCap; }
+    __device__ __forceinline__ void add(bool hot, int slot) {  // warp-collective
+        const unsigned m = __ballot_sync(kFull, hot);
+        if (m == 0u) return;
+        const int c = __popc(m);
+        if (n + c <= kHotCap) {
+            if (hot) slots[n + __popc(m & lt)] = (unsigned short)slot;
+            n += c;
+        } else {
+            n = kHotCap + 1;
+        }
+    }
+};
+
 // 128 consecutive postings of one term, four per lane (lane, lane+32, lane+64, lane+96)
 struct PostingChunk {
     int d0, d1, d2, d3;
@@ -317,17 +346,27 @@ struct PostingChunk {
     }
     __device__ __forceinline__ int doc(int i) const { return i == 0 ? d0 : (i == 1 ? d1 : (i == 2 ? d2 : d3)); }
     // adds the postings with doc < tile_end into the tile; returns how many (a prefix: ids ascend)
-    __device__ __forceinline__ int add_into(float* scw, int base, int tile_end) const {
+    __device__ __forceinline__ int add_into(float* scw, int base, int tile_end, HotList& hl, float theta_f) const {
         const bool in0 = d0 < tile_end, in1 = d1 < tile_end, in2 = d2 < tile_end, in3 = d3 < tile_end;
         // one term has at most one posting per document: the four slots are distinct
-        const float s0 = in0 ? scw[d0 - base] : 0.f;
-        const float s1 = in1 ? scw[d1 - base] : 0.f;
-        const float s2 = in2 ? scw[d2 - base] : 0.f;
-        const float s3 = in3 ? scw[d3 - base] : 0.f;
-        if (in0) scw[d0 - base] = s0 + w0;
-        if (in1) scw[d1 - base] = s1 + w1;
-        if (in2) scw[d2 - base] = s2 + w2;
-        if (in3) scw[d3 - base] = s3 + w3;
+        const float n0 = in0 ? scw[d0 - base] + w0 : 0.f;
+        const float n1 = in1 ? scw[d1 - base] + w1 : 0.f;
+        const float n2 = in2 ? scw[d2 - base] + w2 : 0.f;
+        const float n3 = in3 ? scw[d3 - base] + w3 : 0.f;
+        if (in0) scw[d0 - base] = n0;
+        if (in1) scw[d1 - base] = n1;
+        if (in2) scw[d2 - base] = n2;
+        if (in3) scw[d3 - base] = n3;
+        if (hl.active()) {
+            const bool h0 = in0 && n0 >= theta_f, h1 = in1 && n1 >= theta_f;
+            const bool h2 = in2 && n2 >= theta_f, h3 = in3 && n3 >= theta_f;
+            if (__any_sync(kFull, h0 | h1 | h2 | h3)) {
+                hl.add(h0, d0 - base);
+                hl.add(h1, d1 - base);
+                hl.add(h2, d2 - base);
+                hl.add(h3, d3 - base);
+            }
+        }
         return __popc(__ballot_sync(kFull, in0)) + __popc(__ballot_sync(kFull, in1)) +
                __popc(__ballot_sync(kFull, in2)) + __popc(__ballot_sync(kFull, in3));
     }
@@ -356,7 +395,9 @@ __device__ __forceinline__ bool tile_scan(float* scw, int S, int nd_w, uint32_t 
     return left;
 }
 
-__global__ void __launch_bounds__(512) k_score_topk(const SearchArgs a) {
+// MAXT = 256: up to 8 warps, three CTAs per SM (<= 80 registers); MAXT = 512: up to 16 warps, two CTAs per SM
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const SearchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int NCW = blockDim.x >> 5;
     const int T = a.T, S = a.tile_docs, cap = a.cap;
@@ -365,6 +406,7 @@ __global__ void __launch_bounds__(512) k_score_topk(const SearchArgs a) {
     int* st_pos = reinterpret_cast<int*>(cand + cap);
     int* st_end = st_pos + NCW * T;
     int* st_nxt = st_end + NCW * T;
+    unsigned short* st_hot = reinterpret_cast<unsigned short*>(st_nxt + NCW * T);
     __shared__ int s_ncand, s_overflow;
     __shared__ u64 s_theta;
 
@@ -391,6 +433,7 @@ __global__ void __launch_bounds__(512) k_score_topk(const SearchArgs a) {
     bool leftover = false;       // this warp's tile still holds scores that did not fit in cand
     uint32_t left_doc0 = 0;
     int left_nd = 0;
+    HotList hl{st_hot + warp * kHotCap, kHotCap + 1, (1u << lane) - 1u};
 
     // candidate-buffer overflow round: every warp of the CTA takes part
     auto overflow_round = [&]() {
@@ -432,6 +475,7 @@ __global__ void __launch_bounds__(512) k_score_topk(const SearchArgs a) {
             const int base = j * S;
             const int tile_end = base + S;
             bool touched = false;
+            hl.reset(!a.general && !a.no_hot);
             // ---- accumulate: terms strictly in query order ------------------------------------
             // The terms with a posting in this tile are taken four at a time: the first 32
             // postings of each are requested together (memory-level parallelism across terms),
@@ -465,7 +509,12 @@ __global__ void __launch_bounds__(512) k_score_topk(const SearchArgs a) {
                         int nx = kDocNone;
                         {
                             const bool in = dd[g] < tile_end;
-                            if (in) scw[dd[g] - base] += ww[g];
+                            float nw = 0.f;
+                            if (in) {
+                                nw = scw[dd[g] - base] + ww[g];
+                                scw[dd[g] - base] = nw;
+                            }
+                            if (hl.active()) hl.add(in && nw >= tk.theta_f, dd[g] - base);
                             const int c = __popc(__ballot_sync(kFull, in));
                             p += c;
                             if (c < 32) nx = __shfl_sync(kFull, dd[g], c);
@@ -480,7 +529,7 @@ __global__ void __launch_bounds__(512) k_score_topk(const SearchArgs a) {
                                 A.load(a.ids, a.w, p, e - p, lane);
                                 for (;;) {
                                     B.load(a.ids, a.w, p + 128, e - p - 128, lane);
-                                    const int c = A.add_into(scw, base, tile_end);
+                                    const int c = A.add_into(scw, base, tile_end, hl, tk.theta_f);
                                     p += c;
                                     if (c < 128) {  // the first posting beyond the tile (if any) is element c
                                         nx = __shfl_sync(kFull, A.doc(c >> 5), c & 31);
@@ -495,7 +544,12 @@ __global__ void __launch_bounds__(512) k_score_topk(const SearchArgs a) {
                                     const int d = lane < r ? __ldg(a.ids + p + lane) : kDocNone;
                                     const float w = lane < r ? __ldg(a.w + p + lane) : 0.f;
                                     const bool in = d < tile_end;
-                                    if (in) scw[d - base] += w;
+                                    float nw = 0.f;
+                                    if (in) {
+                                        nw = scw[d - base] + w;
+                                        scw[d - base] = nw;
+                                    }
+                                    if (hl.active()) hl.add(in && nw >= tk.theta_f, d - base);
                                     const int c = __popc(__ballot_sync(kFull, in));
                                     p += c;
                                     if (c < 32) {
@@ -514,11 +568,34 @@ __global__ void __launch_bounds__(512) k_score_topk(const SearchArgs a) {
                     }
                 }
             }
-            // ---- scan + zero the tile, push the documents that beat the k-th best so far ------
+            // ---- epilogue: push the documents that beat the k-th best so far, clear the tile ---
             if (touched || a.general) {
                 const int nd_w = min(S, a.n_docs - base);
-                const bool left = tile_scan(scw, S, nd_w, (uint32_t)base, lane, tk);
-                if (__any_sync(kFull, left)) {
+                bool left = false;
+                if (!hl.active()) {
+                    left = tile_scan(scw, S, nd_w, (uint32_t)base, lane, tk);  // reads, tests and zeroes all S slots
+                } else {
+                    __syncwarp();
+                    for (int i0 = 0; i0 < hl.n; i0 += 32) {
+                        const int i = i0 + lane;
+                        const int x = i < hl.n ? (int)hl.slots[i] : -1 - lane;
+                        const unsigned same = __match_any_sync(kFull, x);  // a slot may be listed twice
+                        if (x >= 0 && (__ffs(same) - 1) == lane) {
+                            const float v = scw[x];
+                            if (v > 0.f) {  // not yet taken by an earlier step of this loop
+                                if (tk.push(v, (uint32_t)(base + x))) scw[x] = 0.f;
+                                else left = true;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    left = __any_sync(kFull, left);
+                    if (!left) {
+                        for (int idx = lane * 4; idx < S; idx += 128)
+                            *reinterpret_cast<float4*>(scw + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                if (__any_sync(kFull, left)) {  // candidate buffer full: the overflow round rescans this tile
                     leftover = true;
                     left_doc0 = (uint32_t)base;
                     left_nd = nd_w;
