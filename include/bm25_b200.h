@@ -73,7 +73,16 @@ int bm25_index_create_device(const int32_t* d_indptr, const int32_t* d_indices, 
 int bm25_index_destroy(bm25_index* index);
 int bm25_index_get_info(const bm25_index* index, bm25_index_info* out);
 
-/* Tuning knobs ("tile_docs", "splits", "force_general", "timing"); 0 restores the default. */
+/* Tuning knobs; value 0 restores the default.  They change how the work is cut, never the result:
+ *   "tile_docs"      documents per warp score tile (multiple of 128; default 2048)
+ *   "consumer_warps" warps (= document chunks) per CTA, 1..16 (default 8)
+ *   "splits"         CTAs per query (default: enough for "waves" waves of resident CTAs)
+ *   "waves"          target number of CTA waves when "splits" is automatic (default 6)
+ *   "cap"            candidate-buffer keys per CTA (default max(2k, 512), power of two)
+ *   "force_general"  1: treat the index as if it held non-positive weights (every doc competes)
+ *   "no_hot" / "no_priming" / "no_theta_share"   1: disable the hot-list epilogue / the load-time
+ *                    threshold priming / the per-query threshold shared between CTAs (A/B switches)
+ *   "timing"         1: record CUDA events around the three kernels of every search */
 int bm25_index_set_option(bm25_index* index, const char* name, int64_t value);
 
 /* With option "timing" = 1 every bm25_search records CUDA events on its stream around its three

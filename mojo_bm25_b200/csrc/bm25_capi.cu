@@ -318,11 +318,6 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
     *lp = LaunchPlan{};
     lp->warps = ix->warps();
     lp->tile_docs = ix->tile_docs();
-    // long queries are bound by per-(tile, term) latency: more, smaller warp tiles per SM
-    if (T >= 32 && ix->opt_warps == 0 && ix->opt_tile_docs == 0 && ix->n_docs >= 16 * 1024) {
-        lp->warps = 16;
-        lp->tile_docs = 1024;
-    }
     lp->cap = ix->opt_cap > 0 ? next_pow2(ix->opt_cap) : next_pow2(std::max(2 * (int64_t)k, (int64_t)512));
     if (lp->cap < k + 64) lp->cap = next_pow2((int64_t)k + 64);
     // shrink the CTA (fewer warps, then smaller tiles) until it fits into shared memory

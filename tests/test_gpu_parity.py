@@ -245,3 +245,33 @@ def test_full_size_config_b_properties(engine):
     # host-buffer entry point returns the same
     hid, hsc = index.search(qn, k)
     assert np.array_equal(hid, ids) and np.array_equal(hsc.view(np.uint32), sc.view(np.uint32))
+
+
+@pytest.mark.parametrize("workload,scale,k", [("B", 0.2, 10), ("10M", 0.02, 100), ("E", 0.1, 1000), ("C", 0.01, 100)])
+def test_every_launch_shape_gives_identical_results(engine, workload, scale, k):
+    """The tuning knobs only change HOW the work is cut (warp tile size, warps per CTA, CTAs per
+    query, candidate-buffer size -> number of overflow rounds, hot-list vs dense epilogue, threshold
+    priming / sharing).  Every variant must return bit-identical ids and scores, and the default must
+    match the oracle."""
+    from mojo_bm25_b200 import synth
+
+    idx, q, _ = synth.make_workload(workload, scale=scale)
+    indptr, indices, data = idx.numpy()
+    q = q.numpy()[:40]
+    k = min(k, idx.n_docs)
+    index = engine.DeviceIndex(indptr, indices, data, n_docs=idx.n_docs)
+    ref_ids, ref_sc = _check_batch(index, indptr, indices, data, idx.n_docs, q[:6], k)
+    ref_ids, ref_sc = index.search(q, k)
+    variants = [
+        dict(cap=k + 64), dict(cap=k + 64, consumer_warps=4, tile_docs=512), dict(no_hot=1), dict(no_priming=1),
+        dict(no_priming=1, cap=k + 64, splits=1), dict(no_theta_share=1, splits=5), dict(consumer_warps=16, tile_docs=1024),
+        dict(consumer_warps=12, tile_docs=4096, splits=2), dict(consumer_warps=1, tile_docs=128, splits=3),
+        dict(waves=1), dict(waves=20, no_hot=1, no_priming=1),
+    ]
+    names = ["cap", "consumer_warps", "tile_docs", "no_hot", "no_priming", "no_theta_share", "splits", "waves"]
+    for v in variants:
+        for n in names:
+            index.set_option(n, v.get(n, 0))
+        ids, sc = index.search(q, k)
+        assert np.array_equal(ids, ref_ids), v
+        assert np.array_equal(sc.view(np.uint32), ref_sc.view(np.uint32)), v
