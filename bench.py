@@ -236,33 +236,52 @@ def run_ours(args):
     mode = args.mode
     if mode == "auto":
         mode = "query-split" if world > 1 and args.workload != "D" else ("doc-shard" if world > 1 else "single")
-    if world == 1:
+    if args.workload == "D" and mode != "query-split":
+        mode = "doc-shard"  # the 100M-doc corpus only exists as 8 document shards, also on one GPU
+    elif world == 1:
         mode = "single"
 
     wl_cfg = synth.WORKLOADS[args.workload]
-    # doc-shard: every rank synthesises ITS shard (seed = rank) of wl n_docs documents (weak in docs);
+    # doc-shard: the corpus is a set of document-range shards, each synthesised with seed = shard
+    #   number and searched through its own int32-indexed handle.  Workload D is a FIXED corpus of 8
+    #   shards x 12.5M docs = 100M docs (3e9 postings): rank r owns shards r, r+W, ... (strong scaling;
+    #   one GPU holds all 8).  Other workloads under --mode doc-shard get one shard per rank (weak).
     # query-split / single: the same index (seed 0) on every rank, rank-specific queries (seed 1+rank).
-    index_seed = rank if mode == "doc-shard" else 0
+    if mode == "doc-shard":
+        total_shards = 8 if args.workload == "D" else world
+        if total_shards % world:
+            raise SystemExit(f"workload D has 8 document shards; --gpus must divide 8 (got {world})")
+        my_shards = list(range(rank, total_shards, world))
+    else:
+        total_shards, my_shards = 1, [0]
     query_seed = 1 if mode == "doc-shard" else 1 + rank
-    idx, q, k = synth.make_workload(args.workload, device=str(dev), index_seed=index_seed, query_seed=query_seed,
-                                    scale=args.scale)
+    indexes, synths, q, k = [], [], None, None
+    for sh in my_shards:
+        idx, q, k = synth.make_workload(args.workload, device=str(dev), index_seed=sh, query_seed=query_seed,
+                                        scale=args.scale)
+        base = sh * idx.n_docs if mode == "doc-shard" else 0
+        ix = engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs, doc_id_base=base)
+        ix.set_option("timing", 1)
+        indexes.append(ix)
+        synths.append(idx)
     if args.k:
         k = args.k
-    base = rank * idx.n_docs if mode == "doc-shard" else 0
-    index = engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs, doc_id_base=base)
-    index.set_option("timing", 1)
+    idx, index = synths[0], indexes[0]
     qn = q.cpu().numpy()
     n_q = q.shape[0]
-    posting_bytes = index.posting_bytes(qn, 0)  # 8 * sum df  (score-accumulation kernel)
+    posting_bytes = sum(ix.posting_bytes(qn, 0) for ix in indexes)  # 8 * sum df (score kernel)
     batch_bytes = posting_bytes + 8 * k * n_q
     out_ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
     out_sc = torch.empty((n_q, k), dtype=torch.float32, device=dev)
-    searcher = sharded.DocShardedSearcher.from_index(index, k) if mode == "doc-shard" else None
+    searcher = sharded.DocShardedSearcher.from_index(indexes, k) if mode == "doc-shard" else None
 
     def step():
         if searcher is not None:
             return searcher.search(q)
         return index.search_device(q, k, out_ids=out_ids, out_scores=out_sc)
+
+    def kernel_ms():  # (segments, score, merge) device ms of this rank's last step, summed over its shards
+        return tuple(map(sum, zip(*[ix.last_timing_ms() for ix in indexes])))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for _ in range(args.warmup):
@@ -285,7 +304,7 @@ def run_ours(args):
         starts[i].record()
         step()
         ends[i].record()
-        kern_ms.append(index.last_timing_ms())  # waits for this step's kernels (device events)
+        kern_ms.append(kernel_ms())  # waits for this step's kernels (device events)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -321,24 +340,27 @@ def run_ours(args):
         e2e = {"value": units / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(qn.nbytes),
                "d2h_bytes_per_step": int(hid.nbytes + hsc.nbytes), "api": "bm25_search_host via DeviceIndex.search"}
     else:
-        # doc-shard e2e: pinned queries -> H2D -> local search -> all-gather -> merge -> D2H of the result
+        # doc-shard e2e: pinned queries -> H2D -> local search(es) -> all-gather -> merge -> D2H of the result
         q_pin = torch.from_numpy(qn).pin_memory()
         q_dev = torch.empty_like(q)
         for w in range(2 + args.steps):
             if w == 2:
                 torch.cuda.synchronize()
-                dist.barrier()
+                if dist is not None:
+                    dist.barrier()
                 t0 = time.perf_counter()
             flush.zero_()
             q_dev.copy_(q_pin, non_blocking=True)
             gi, gs = searcher.search(q_dev)
             hid, hsc = gi.cpu(), gs.cpu()
         e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": units / (float(t.item()) / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(qn.nbytes),
+        if dist is not None:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": units / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(qn.nbytes),
                "d2h_bytes_per_step": int(hid.numel() * 4 + hsc.numel() * 4),
-               "api": "DocShardedSearcher.search (bm25_search + all_gather + bm25_merge_topk)"}
+               "api": "DocShardedSearcher.search (bm25_search per shard + all_gather + bm25_merge_topk)"}
     clocks = sampler.stop()
 
     if rank != 0:
@@ -379,18 +401,23 @@ def run_ours(args):
         n_sample = cpu_sample_size(n_q, idx.n_docs, cores, args.cpu_sample)
         indptr, indices, data = idx.numpy()
         res = run_cpu_port(indptr, indices, data, idx.n_docs, qn[:n_sample], k, 1, 0)
-        cpu = {"value": res["qps"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+        cpu = {"value": res["qps"] / total_shards, "unit": UNIT, "cores": res["cores"], "kind": "port",
                "sample": f"first {n_sample} of {n_q} queries of the same batch, oracle port of BM25v.search, "
-                         f"{res['cores']} forked workers, {res['step_seconds'][0]:.2f} s"}
+                         f"{res['cores']} forked workers, {res['step_seconds'][0]:.2f} s"
+                         + (f"; timed on shard 0 of {total_shards} and divided by {total_shards} (a query visits every shard)"
+                            if total_shards > 1 else "")}
 
     par = {"single": "1 GPU", "query-split": f"query-split x{world}: index replicated, each rank answers its own "
            f"{n_q}-query batch, no data-path collective",
-           "doc-shard": f"doc-shard x{world}: {idx.n_docs} docs per rank ({idx.n_docs * world} total), same batch on "
-           "every rank, local top-k + NCCL all-gather + merge kernel"}[mode]
+           "doc-shard": f"doc-shard x{world}: {total_shards} shards of {idx.n_docs} docs ({idx.n_docs * total_shards} "
+           f"total), {len(my_shards)} per rank, same batch on every rank, local top-k + NCCL all-gather of "
+           f"{n_q * k * 8 * len(my_shards)} B per rank + merge kernel"}[mode]
+    strong = mode == "doc-shard" and args.workload == "D"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
-        "data": "synthetic", "config": workload_config(args, wl_cfg, idx, q, k, {"parallelism": par}),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": DTYPE,
+        "data": "synthetic", "config": workload_config(args, wl_cfg, idx, q, k, {"parallelism": par, "shards": total_shards}),
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         "wall_s_timed_region": wall, "step_ms_min": float(min(step_ms)), "step_ms_median": float(np.median(step_ms)),
     }

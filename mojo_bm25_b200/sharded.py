@@ -30,12 +30,15 @@ def doc_range_of_rank(n_docs: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 class DocShardedSearcher:
-    def __init__(self, local_search: Callable, k: int, merge: Optional[Callable] = None,
+    def __init__(self, local_search, k: int, merge: Optional[Callable] = None,
                  group: Optional[dist.ProcessGroup] = None):
         """``local_search(queries, k, out_ids, out_scores)`` fills the two [Q,k] outputs with the
-        shard-local top-k (GLOBAL doc ids).  ``merge(ids_view, scores_view, k, list_stride,
-        n_lists, n_queries, k_in)`` defaults to the CUDA merge kernel."""
-        self.local_search = local_search
+        shard-local top-k (GLOBAL doc ids); pass a LIST of such callables when this rank owns
+        several document shards (a corpus of more than 2^31 postings on few GPUs: every shard is
+        its own int32-indexed handle).  Every rank must own the same number of shards.
+        ``merge(ids_view, scores_view, k, list_stride, n_lists, n_queries, k_in)`` defaults to the
+        CUDA merge kernel."""
+        self.local_searches = list(local_search) if isinstance(local_search, (list, tuple)) else [local_search]
         self.k = int(k)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -49,10 +52,17 @@ class DocShardedSearcher:
 
     @classmethod
     def from_index(cls, index, k: int, group=None):
-        return cls(lambda q, kk, oi, os_: index.search_device(q, kk, out_ids=oi, out_scores=os_), k, group=group)
+        """``index``: one DeviceIndex, or the list of DeviceIndex shards this rank owns."""
+        idxs = list(index) if isinstance(index, (list, tuple)) else [index]
+
+        def make(ix):
+            return lambda q, kk, oi, os_: ix.search_device(q, kk, out_ids=oi, out_scores=os_)
+
+        return cls([make(ix) for ix in idxs], k, group=group)
 
     def _buffers(self, n_queries: int, device):
-        shape = (2, n_queries, self.k)
+        n_local = len(self.local_searches)
+        shape = (n_local, 2, n_queries, self.k)
         if self._send is None or self._send.shape != shape or self._send.device != device:
             self._send = torch.empty(shape, dtype=torch.int32, device=device)
             self._recv = torch.empty((self.world,) + shape, dtype=torch.int32, device=device)
@@ -61,14 +71,17 @@ class DocShardedSearcher:
     def search(self, queries: torch.Tensor):
         """queries int32 [Q,T] (identical on all ranks) -> global (ids [Q,k], scores [Q,k])."""
         n_queries = queries.shape[0]
+        n_local = len(self.local_searches)
         send, recv = self._buffers(n_queries, queries.device)
-        self.local_search(queries, self.k, send[0], send[1].view(torch.float32))
+        for s, local in enumerate(self.local_searches):
+            local(queries, self.k, send[s, 0], send[s, 1].view(torch.float32))
         if self.world > 1:
-            dist.all_gather_into_tensor(recv.view(self.world * 2, n_queries, self.k), send, group=self.group)
+            dist.all_gather_into_tensor(recv.view(self.world * n_local * 2, n_queries, self.k),
+                                        send.view(n_local * 2, n_queries, self.k), group=self.group)
         else:
             recv[0].copy_(send)
-        return self.merge(recv[0, 0], recv[0, 1].view(torch.float32), self.k,
-                          list_stride=2 * n_queries * self.k, n_lists=self.world,
+        return self.merge(recv[0, 0, 0], recv[0, 0, 1].view(torch.float32), self.k,
+                          list_stride=2 * n_queries * self.k, n_lists=self.world * n_local,
                           n_queries=n_queries, k_in=self.k)
 
 

@@ -275,3 +275,27 @@ def test_every_launch_shape_gives_identical_results(engine, workload, scale, k):
         ids, sc = index.search(q, k)
         assert np.array_equal(ids, ref_ids), v
         assert np.array_equal(sc.view(np.uint32), ref_sc.view(np.uint32)), v
+
+
+def test_degenerate_shapes(engine):
+    """Empty index, all-padding queries, T = 1, k = n_docs, a wide query row, a single document."""
+    # empty index (no postings at all): every document scores 0 and the first k ids come back
+    index = engine.DeviceIndex(np.zeros(6, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32), n_docs=300)
+    ids, sc = index.search(np.array([[0, 4, -1]], np.int32), 7)
+    assert ids.tolist() == [list(range(7))] and not sc.any()
+    # one document, one term
+    index = engine.DeviceIndex(np.array([0, 1], np.int32), np.array([0], np.int32), np.array([2.5], np.float32), n_docs=1)
+    ids, sc = index.search(np.array([[0], [-1]], np.int32), 1)
+    assert ids.tolist() == [[0], [0]] and sc.tolist() == [[2.5], [0.0]]
+    # k = n_docs and a 200-slot query row (mostly padding, duplicated terms count with multiplicity)
+    rng = np.random.default_rng(3)
+    import scipy.sparse as sp
+
+    m = sp.random(700, 40, density=0.2, format="csc", dtype=np.float32, random_state=np.random.RandomState(9),
+                  data_rvs=lambda n: (0.05 + rng.random(n)).astype(np.float32))
+    m.sort_indices()
+    index = engine.DeviceIndex(m.indptr, m.indices, m.data, n_docs=700)
+    q = np.full((5, 200), -1, np.int32)
+    q[:, ::7] = rng.integers(0, 40, size=(5, 29))
+    _check_batch(index, m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data, 700, q, 700)
+    _check_batch(index, m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data, 700, q, 3)

@@ -60,6 +60,21 @@ def _worker(rank, world, port, mode, ret):
 
         s = sharded.DocShardedSearcher(local, k, merge=_oracle_merge)
         ids, sc = s.search(qt)
+    elif mode == "doc2":  # two document shards per rank (a fixed 4-shard corpus on 2 ranks)
+        parts = orc.partition_csc_by_doc_range(indptr, indices, data, n_docs, 2 * world)
+
+        def make(part):
+            ptr, ind, dat, nd, base = part
+
+            def local(queries, kk, out_ids, out_scores):
+                i, s = orc.search_csc(ptr, ind, dat, nd, queries.numpy(), kk)
+                out_ids.copy_(torch.from_numpy(i + base))
+                out_scores.copy_(torch.from_numpy(s))
+
+            return local
+
+        s = sharded.DocShardedSearcher([make(parts[rank]), make(parts[rank + world])], k, merge=_oracle_merge)
+        ids, sc = s.search(qt)
     else:
         def local(queries, kk, out_ids, out_scores):
             i, s = orc.search_csc(indptr, indices, data, n_docs, queries.numpy(), kk)
@@ -73,7 +88,7 @@ def _worker(rank, world, port, mode, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["doc", "query"])
+@pytest.mark.parametrize("mode", ["doc", "doc2", "query"])
 def test_sharded_search_world2(mode):
     world = 2
     port = _free_port()
