@@ -159,7 +159,7 @@ struct bm25_index {
     std::vector<int32_t> h_indptr;  // host copy for byte accounting / validation
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
-    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0;
+    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_wide_min = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace
@@ -464,6 +464,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.cap = lp.cap;
     a.general = lp.general;
     a.no_hot = ix->opt_no_hot;
+    a.wide_min = ix->opt_wide_min > 0 ? ix->opt_wide_min : 64;
     if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
     MergeArgs m{};
@@ -711,6 +712,9 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
         ix->opt_no_theta_share = value ? 1 : 0;
     } else if (!strcmp(name, "no_priming")) {
         ix->opt_no_priming = value ? 1 : 0;
+    } else if (!strcmp(name, "wide_min")) {
+        if (value < 0 || value > (1 << 20)) return fail(BM25_ERR_INVALID, "wide_min out of range");
+        ix->opt_wide_min = (int)value;
     } else if (!strcmp(name, "no_hot")) {
         ix->opt_no_hot = value ? 1 : 0;
     } else if (!strcmp(name, "force_general")) {

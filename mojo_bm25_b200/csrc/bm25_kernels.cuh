@@ -181,6 +181,7 @@ struct SearchArgs {
     int splits, tiles_per_split, cap;     // splits = CTAs per query (tiles_per_split: k_scores_dense)
     int general;                          // 1: zero-score docs compete (weights may be <= 0)
     int no_hot;                           // 1: always use the dense tile scan (A/B switch)
+    int wide_min;                         // average postings per tile from which a term takes the 128-wide path
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -477,88 +478,88 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
             bool touched = false;
             hl.reset(!a.general && !a.no_hot);
             // ---- accumulate: terms strictly in query order ------------------------------------
-            // The terms with a posting in this tile are taken four at a time: the first 32
-            // postings of each are requested together (memory-level parallelism across terms),
-            // then added one term after the other.
+            // Dense terms (>= wide_min postings per remaining tile on average) stream 128 postings
+            // per step with the next step's loads already in flight.  Runs of sparse terms are taken
+            // up to four at a time: the first 32 postings of each are requested together
+            // (memory-level parallelism across terms), then added one term after the other.
+            const int wide_cut = a.wide_min * (j1 - j);
             for (int g0 = 0; g0 < T; g0 += 32) {
                 const int tl = g0 + lane;
                 unsigned act = __ballot_sync(kFull, tl < T && nxt_w[min(tl, T - 1)] < tile_end);
                 if (act) touched = true;
                 while (act) {
-                    int tt[4], pp[4], ee[4], dd[4];
+                    const int t0 = g0 + __ffs(act) - 1;
+                    int p = pos_w[t0];
+                    int e = end_w[t0];
+                    if (e - p >= wide_cut) {
+                        act &= act - 1;
+                        int nx = kDocNone;
+                        PostingChunk A, B;
+                        A.load(a.ids, a.w, p, e - p, lane);
+                        for (;;) {
+                            B.load(a.ids, a.w, p + 128, e - p - 128, lane);
+                            const int c = A.add_into(scw, base, tile_end, hl, tk.theta_f);
+                            p += c;
+                            if (c < 128) {  // the first posting beyond the tile (if any) is element c
+                                nx = __shfl_sync(kFull, A.doc(c >> 5), c & 31);
+                                break;
+                            }
+                            if (p >= e) break;
+                            A = B;
+                        }
+                        if (lane == 0) {
+                            pos_w[t0] = p;
+                            nxt_w[t0] = nx;
+                        }
+                        __syncwarp();
+                        continue;
+                    }
+                    int tt[4] = {-1, -1, -1, -1}, pp[4], ee[4], dd[4];
                     float ww[4];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        tt[g] = -1;
                         if (act) {
                             const int t = g0 + __ffs(act) - 1;
-                            act &= act - 1;
-                            tt[g] = t;
-                            pp[g] = pos_w[t];
-                            ee[g] = end_w[t];
-                            const int r = ee[g] - pp[g];
-                            dd[g] = lane < r ? __ldg(a.ids + pp[g] + lane) : kDocNone;
-                            ww[g] = lane < r ? __ldg(a.w + pp[g] + lane) : 0.f;
+                            const int pt = pos_w[t], et = end_w[t];
+                            const int r = et - pt;
+                            if (g == 0 || r < wide_cut) {  // a dense term ends the run (handled above next)
+                                act &= act - 1;
+                                tt[g] = t;
+                                pp[g] = pt;
+                                ee[g] = et;
+                                dd[g] = lane < r ? __ldg(a.ids + pt + lane) : kDocNone;
+                                ww[g] = lane < r ? __ldg(a.w + pt + lane) : 0.f;
+                            } else {
+                                break;
+                            }
                         }
                     }
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         if (tt[g] < 0) break;  // warp-uniform
-                        int p = pp[g];
-                        const int e = ee[g];
+                        p = pp[g];
+                        e = ee[g];
                         int nx = kDocNone;
-                        {
-                            const bool in = dd[g] < tile_end;
+                        int d = dd[g];
+                        float w = ww[g];
+                        for (;;) {
+                            const bool in = d < tile_end;
                             float nw = 0.f;
                             if (in) {
-                                nw = scw[dd[g] - base] + ww[g];
-                                scw[dd[g] - base] = nw;
+                                nw = scw[d - base] + w;
+                                scw[d - base] = nw;
                             }
-                            if (hl.active()) hl.add(in && nw >= tk.theta_f, dd[g] - base);
+                            if (hl.active()) hl.add(in && nw >= tk.theta_f, d - base);
                             const int c = __popc(__ballot_sync(kFull, in));
                             p += c;
-                            if (c < 32) nx = __shfl_sync(kFull, dd[g], c);
-                            else if (p < e) nx = -1;  // more of this term may lie in the tile
-                        }
-                        if (nx == -1) {
-                            nx = kDocNone;
-                            if ((e - p) >= 64 * (j1 - j)) {
-                                // dense term (>= 64 postings per remaining tile on average): 128
-                                // postings per step, the next step's loads already in flight
-                                PostingChunk A, B;
-                                A.load(a.ids, a.w, p, e - p, lane);
-                                for (;;) {
-                                    B.load(a.ids, a.w, p + 128, e - p - 128, lane);
-                                    const int c = A.add_into(scw, base, tile_end, hl, tk.theta_f);
-                                    p += c;
-                                    if (c < 128) {  // the first posting beyond the tile (if any) is element c
-                                        nx = __shfl_sync(kFull, A.doc(c >> 5), c & 31);
-                                        break;
-                                    }
-                                    if (p >= e) break;
-                                    A = B;
-                                }
-                            } else {
-                                for (;;) {
-                                    const int r = e - p;  // > 0
-                                    const int d = lane < r ? __ldg(a.ids + p + lane) : kDocNone;
-                                    const float w = lane < r ? __ldg(a.w + p + lane) : 0.f;
-                                    const bool in = d < tile_end;
-                                    float nw = 0.f;
-                                    if (in) {
-                                        nw = scw[d - base] + w;
-                                        scw[d - base] = nw;
-                                    }
-                                    if (hl.active()) hl.add(in && nw >= tk.theta_f, d - base);
-                                    const int c = __popc(__ballot_sync(kFull, in));
-                                    p += c;
-                                    if (c < 32) {
-                                        nx = __shfl_sync(kFull, d, c);
-                                        break;
-                                    }
-                                    if (p >= e) break;
-                                }
+                            if (c < 32) {
+                                nx = __shfl_sync(kFull, d, c);
+                                break;
                             }
+                            if (p >= e) break;
+                            const int r = e - p;
+                            d = lane < r ? __ldg(a.ids + p + lane) : kDocNone;
+                            w = lane < r ? __ldg(a.w + p + lane) : 0.f;
                         }
                         if (lane == 0) {
                             pos_w[tt[g]] = p;
