@@ -23,8 +23,7 @@ namespace bm25 {
 
 typedef unsigned long long u64;
 
-constexpr int kThreads = 512;          // threads per CTA of k_score_topk / k_merge
-constexpr int kChunk = kThreads * 4;   // documents scanned per block-wide step (float4 / thread)
+constexpr int kThreads = 512;          // threads per CTA of k_merge / k_scores_dense
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kBoundLevels = 11;       // per-term weight order statistics at ranks 1, 2, 4, ..., 1024
 constexpr int kBoundSample = 1024;     // postings sampled per term for those statistics
@@ -102,13 +101,14 @@ __global__ void __launch_bounds__(256) k_segments(const int32_t* __restrict__ in
 }
 
 // ---------------------------------------------------------------------------------------------
-// group barriers: the whole CTA (barrier 0) or the consumer warps of k_score_topk (barrier 1)
+// group barriers: __syncthreads (barrier 0), or named barrier 1 over the warps of k_score_topk --
+// its warps reach the (rare) candidate-compaction rounds from different places in their tile loops
 // ---------------------------------------------------------------------------------------------
 struct CtaGroup {
     int size, rank;
     __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
-struct ConsumerGroup {
+struct WarpsGroup {
     int size, rank;
     __device__ __forceinline__ void sync() const {
         asm volatile("bar.sync 1, %0;" ::"r"(size) : "memory");
@@ -220,37 +220,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_scores_dense(const SearchArgs a
         for (int i = tid; i < nd; i += kThreads) { out[i] = sc[i]; sc[i] = 0.f; }
         __syncthreads();
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// mbarrier / bulk-copy (TMA 1-D) primitives
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(u64* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// global -> shared bulk async copy; completion counted in bytes on `bar` (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, u64* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -417,7 +386,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     const int q = blockIdx.x / a.splits;
     const int sp = blockIdx.x - q * a.splits;
     const int chunk = sp * NCW + warp;
-    const ConsumerGroup grp{(int)blockDim.x, tid};
+    const WarpsGroup grp{(int)blockDim.x, tid};
 
     float* scw = sc + (size_t)warp * S;
     for (int i = lane * 4; i < S; i += 128) *reinterpret_cast<float4*>(scw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
