@@ -336,7 +336,8 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
     if (splits <= 0) {
         const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>((int64_t)(ix->smem_per_sm - 1024) / (int64_t)(lp->smem + 1024),
                                                                       2048 / (lp->warps * 32)));
-        const int64_t waves = ix->opt_waves > 0 ? ix->opt_waves : 10;
+        // finer CTAs balance the tail; with a large k every CTA pays for big candidate sorts, so fewer
+        const int64_t waves = ix->opt_waves > 0 ? ix->opt_waves : (k > 256 ? 6 : 10);
         const int64_t want = waves * per_sm * ix->sm_count;  // CTAs in flight x waves
         splits = (int)std::max<int64_t>(1, (want + Q - 1) / std::max<int64_t>(Q, 1));
     }
