@@ -77,8 +77,8 @@ int bm25_index_get_info(const bm25_index* index, bm25_index_info* out);
  *   "tile_docs"      documents per warp score tile (multiple of 128; default 2048)
  *   "consumer_warps" warps (= document chunks) per CTA, 1..16 (default 8)
  *   "splits"         CTAs per query (default: enough for "waves" waves of resident CTAs)
- *   "waves"          target number of CTA waves when "splits" is automatic (default 10; 6 for k > 256)
- *   "cap"            candidate-buffer keys per CTA (default max(2k, 512), power of two)
+ *   "waves"          target number of CTA waves when "splits" is automatic (default 10; 4 for k > 256)
+ *   "cap"            candidate-buffer keys per CTA (default max(4k, 512) up to k = 1024, else 2k; power of two)
  *   "force_general"  1: treat the index as if it held non-positive weights (every doc competes)
  *   "no_hot" / "no_priming" / "no_theta_share"   1: disable the hot-list epilogue / the load-time
  *                    threshold priming / the per-query threshold shared between CTAs (A/B switches)

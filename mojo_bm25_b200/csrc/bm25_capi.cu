@@ -318,7 +318,8 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
     *lp = LaunchPlan{};
     lp->warps = ix->warps();
     lp->tile_docs = ix->tile_docs();
-    lp->cap = ix->opt_cap > 0 ? next_pow2(ix->opt_cap) : next_pow2(std::max(2 * (int64_t)k, (int64_t)512));
+    lp->cap = ix->opt_cap > 0 ? next_pow2(ix->opt_cap)
+                              : next_pow2(std::max((k <= 1024 ? 4 : 2) * (int64_t)k, (int64_t)512));
     if (lp->cap < k + 64) lp->cap = next_pow2((int64_t)k + 64);
     // shrink the CTA (fewer warps, then smaller tiles) until it fits into shared memory
     const size_t hard = ix->smem_optin - 1024;
@@ -337,7 +338,7 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
         const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>((int64_t)(ix->smem_per_sm - 1024) / (int64_t)(lp->smem + 1024),
                                                                       2048 / (lp->warps * 32)));
         // finer CTAs balance the tail; with a large k every CTA pays for big candidate sorts, so fewer
-        const int64_t waves = ix->opt_waves > 0 ? ix->opt_waves : (k > 256 ? 6 : 10);
+        const int64_t waves = ix->opt_waves > 0 ? ix->opt_waves : (k > 256 ? 4 : 10);
         const int64_t want = waves * per_sm * ix->sm_count;  // CTAs in flight x waves
         splits = (int)std::max<int64_t>(1, (want + Q - 1) / std::max<int64_t>(Q, 1));
     }
