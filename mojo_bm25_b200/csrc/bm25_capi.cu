@@ -159,7 +159,7 @@ struct bm25_index {
     std::vector<int32_t> h_indptr;  // host copy for byte accounting / validation
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
-    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_wide_min = 0, opt_kernel = 0, opt_cta_tile = 0, opt_stage = 0, opt_stages = 0;
+    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_wide_min = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace
@@ -273,7 +273,6 @@ int canonicalise_host(const int32_t* indptr, const int32_t* indices, const float
 struct LaunchPlan {
     int tile_docs, n_tiles, splits, tiles_per_split, cap, warps, general;
     int tiles_per_chunk, n_chunks;  // k_score_topk: a chunk = the tiles one warp walks
-    int cta_kernel, stage, stages;  // k_score_topk_cta: shared tile + staging ring
     int seg_docs, seg_rows;         // granularity / row count of the segment table
     size_t smem;
     u64 theta0;
@@ -312,51 +311,6 @@ int make_plan_dense(bm25_index* ix, int64_t Q, int64_t T, LaunchPlan* lp) {
     lp->seg_docs = lp->tile_docs;
     lp->seg_rows = lp->n_tiles;
     plan_mode(ix, lp);
-    return BM25_OK;
-}
-
-constexpr int kCtaWarps = 8;  // consumer warps of k_score_topk_cta
-
-size_t score_smem_cta(int tile_docs, int stage, int stages, int cap, int64_t T) {
-    return (size_t)tile_docs * 4 + (size_t)stages * stage * 8 + (size_t)cap * 8 + 2 * kMaxStages * 8 +
-           kMaxStages * 4 * 4 + (size_t)stages * T * 8 + (size_t)T * 8 + kHotCta * 2 + 128;
-}
-
-// k_score_topk_cta: CTA = (query, range of shared 16K-document tiles)
-int make_plan_cta(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
-    *lp = LaunchPlan{};
-    plan_mode(ix, lp);
-    lp->cta_kernel = 1;
-    lp->warps = kCtaWarps;
-    int t = ix->opt_cta_tile > 0 ? ix->opt_cta_tile : 16384;
-    const int64_t need = std::max<int64_t>(((ix->n_docs + 1023) / 1024) * 1024, 1024);
-    if (need < t) t = (int)need;
-    lp->tile_docs = ((t + 1023) / 1024) * 1024;
-    lp->stage = ix->opt_stage > 0 ? ((ix->opt_stage + 3) / 4) * 4 : 2048;
-    lp->stages = ix->opt_stages > 0 ? ix->opt_stages : 2;
-    lp->cap = ix->opt_cap > 0 ? next_pow2(ix->opt_cap)
-                              : next_pow2(std::max((k <= 1024 ? 4 : 2) * (int64_t)k, (int64_t)512));
-    if (lp->cap < k + 64) lp->cap = next_pow2((int64_t)k + 64);
-    const size_t hard = ix->smem_optin - 1024;
-    for (;;) {
-        lp->smem = score_smem_cta(lp->tile_docs, lp->stage, lp->stages, lp->cap, T);
-        if (lp->smem <= hard) break;
-        if (lp->tile_docs > 1024) { lp->tile_docs -= 1024; continue; }
-        return fail(BM25_ERR_UNSUPPORTED, "query shape (T=%lld, k=%d) does not fit in shared memory",
-                    (long long)T, k);
-    }
-    lp->n_tiles = (int)std::max<int64_t>(1, (ix->n_docs + lp->tile_docs - 1) / lp->tile_docs);
-    int splits = ix->opt_splits;
-    if (splits <= 0) {
-        const int64_t per_sm = std::max<int64_t>(1, (int64_t)(ix->smem_per_sm - 1024) / (int64_t)(lp->smem + 1024));
-        const int64_t waves = ix->opt_waves > 0 ? ix->opt_waves : (k > 256 ? 4 : 10);
-        splits = (int)std::max<int64_t>(1, (waves * per_sm * ix->sm_count + Q - 1) / std::max<int64_t>(Q, 1));
-    }
-    splits = std::max(1, std::min(splits, lp->n_tiles));
-    lp->tiles_per_split = (lp->n_tiles + splits - 1) / splits;
-    lp->splits = (lp->n_tiles + lp->tiles_per_split - 1) / lp->tiles_per_split;
-    lp->seg_docs = lp->tile_docs;
-    lp->seg_rows = lp->n_tiles;
     return BM25_OK;
 }
 
@@ -420,11 +374,7 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
         k_scores_dense<<<(unsigned)grid, kThreads, lp.smem, st>>>(a);
     } else {
         static thread_local size_t configured[2][64] = {{0}, {0}};
-        static thread_local size_t configured_cta[64] = {0};
-        if (lp.cta_kernel) {
-            if ((rc = configure_smem(k_score_topk_cta<kCtaWarps>, lp.smem, ix->smem_optin, &configured_cta[ix->device % 64]))) return rc;
-            k_score_topk_cta<kCtaWarps><<<(unsigned)grid, (kCtaWarps + 1) * 32, lp.smem, st>>>(a);
-        } else if (lp.warps <= 8) {
+        if (lp.warps <= 8) {
             if ((rc = configure_smem(k_score_topk<256>, lp.smem, ix->smem_optin, &configured[0][ix->device % 64]))) return rc;
             k_score_topk<256><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
         } else {
@@ -480,8 +430,7 @@ int merge_P(int64_t total, int k_out) {
 int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T, int k, int32_t* d_out_ids,
                   float* d_out_scores, cudaStream_t st) {
     LaunchPlan lp;
-    const bool use_cta = ix->opt_kernel == 2;  // auto (0) = the warp-per-chunk kernel
-    int rc = use_cta ? make_plan_cta(ix, Q, T, k, &lp) : make_plan(ix, Q, T, k, &lp);
+    int rc = make_plan(ix, Q, T, k, &lp);
     if (rc) return rc;
     if ((rc = ix->ws_partial.reserve((size_t)Q * lp.splits * k))) return rc;
     if ((rc = ix->ws_theta.reserve((size_t)Q))) return rc;
@@ -513,9 +462,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.tiles_per_chunk = lp.tiles_per_chunk;
     a.n_chunks = lp.n_chunks;
     a.splits = lp.splits;
-    a.tiles_per_split = lp.tiles_per_split;
-    a.stage_postings = lp.stage;
-    a.n_stages = lp.stages;
+    a.tiles_per_split = 0;
     a.cap = lp.cap;
     a.general = lp.general;
     a.no_hot = ix->opt_no_hot;
@@ -770,18 +717,6 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
     } else if (!strcmp(name, "wide_min")) {
         if (value < 0 || value > (1 << 20)) return fail(BM25_ERR_INVALID, "wide_min out of range");
         ix->opt_wide_min = (int)value;
-    } else if (!strcmp(name, "kernel")) {
-        if (value < 0 || value > 2) return fail(BM25_ERR_INVALID, "kernel must be 0 (auto), 1 (warp) or 2 (cta)");
-        ix->opt_kernel = (int)value;
-    } else if (!strcmp(name, "cta_tile_docs")) {
-        if (value < 0 || value > (1 << 16)) return fail(BM25_ERR_INVALID, "cta_tile_docs out of range");
-        ix->opt_cta_tile = (int)value;
-    } else if (!strcmp(name, "stage_postings")) {
-        if (value < 0 || value > (1 << 15)) return fail(BM25_ERR_INVALID, "stage_postings out of range");
-        ix->opt_stage = (int)value;
-    } else if (!strcmp(name, "stages")) {
-        if (value != 0 && (value < 2 || value > kMaxStages)) return fail(BM25_ERR_INVALID, "stages must be 0 or 2..4");
-        ix->opt_stages = (int)value;
     } else if (!strcmp(name, "no_hot")) {
         ix->opt_no_hot = value ? 1 : 0;
     } else if (!strcmp(name, "force_general")) {

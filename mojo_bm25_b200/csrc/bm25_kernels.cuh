@@ -181,7 +181,6 @@ struct SearchArgs {
     int splits, tiles_per_split, cap;     // splits = CTAs per query (tiles_per_split: k_scores_dense)
     int general;                          // 1: zero-score docs compete (weights may be <= 0)
     int no_hot;                           // 1: always use the dense tile scan (A/B switch)
-    int stage_postings, n_stages;         // k_score_topk_cta: staging ring geometry
     int wide_min;                         // average postings per tile from which a term takes the 128-wide path
 };
 
@@ -588,319 +587,6 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     const int n = s_ncand;
     u64* out = a.partial + ((int64_t)q * a.splits + sp) * a.k;
     for (int i = tid; i < a.k; i += blockDim.x) out[i] = (i < n) ? cand[i] : 0ull;
-}
-
-// ---------------------------------------------------------------------------------------------
-// mbarrier / bulk-copy (TMA 1-D) primitives
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(u64* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// global -> shared bulk async copy; completion counted in bytes on `bar` (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, u64* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_score_topk_cta: CTA-cooperative variant of the hot kernel for short queries.
-//
-// CTA = (query, range of document tiles).  The whole CTA shares ONE score tile of tile_docs
-// (16K) documents, so a (tile, term) step amortises its bookkeeping over 8x more postings than in
-// the warp-per-chunk kernel; the price is a named barrier between the terms of a tile.
-//   producer warp : walks the tiles, packs the query terms' posting segments of a tile (from the
-//                   tile-major segment table) into rounds that fit one staging buffer and issues
-//                   them as 1-D bulk async copies (TMA, UBLKCP) into an NS-stage shared-memory
-//                   ring; completion on mbarriers.  Loads run a whole stage ahead of the adds.
-//   consumer warps: wait for a round and add its pieces into the score tile strictly in
-//                   query-term order: a piece of more than kSmallPiece postings is spread over all
-//                   consumer threads (four postings per thread in flight; a term has at most one
-//                   posting per document, so no atomics) followed by one named barrier; a RUN of
-//                   small pieces is added by warp 0 alone, piece after piece, and costs a single
-//                   barrier however many terms it holds.  Slots whose running score reaches the
-//                   pre-filter threshold go to the CTA's hot list; the tile epilogue pushes them
-//                   into the candidate buffer and clears the tile with 16-byte stores (dense scan
-//                   if the list overflowed or the index has non-positive weights).
-// shared memory (dynamic):
-//   float score[tile_docs] | int32 st_ids[NS][stg] | float st_w[NS][stg] | u64 cand[cap]
-//   | u64 full[4], empty[4] | int rd[4][4] | int pc_so[NS][T] | int pc_cnt[NS][T] | int p_lo[T], p_hi[T]
-//   | uint16 hot[kHotCta]
-// ---------------------------------------------------------------------------------------------
-constexpr int kSmallPiece = 64;
-constexpr int kHotCta = 512;
-constexpr int kMaxStages = 4;
-
-template <int NCW>
-__global__ void __launch_bounds__((NCW + 1) * 32, 2) k_score_topk_cta(const SearchArgs a) {
-    constexpr int NC = NCW * 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int T = a.T, stg = a.stage_postings, cap = a.cap, NS = a.n_stages;
-    float* sc = reinterpret_cast<float*>(smem_raw);
-    int32_t* st_ids = reinterpret_cast<int32_t*>(smem_raw + (size_t)a.tile_docs * 4);
-    float* st_w = reinterpret_cast<float*>(st_ids + NS * stg);
-    u64* cand = reinterpret_cast<u64*>(st_w + NS * stg);
-    u64* bar_full = cand + cap;
-    u64* bar_empty = bar_full + kMaxStages;
-    int* rd = reinterpret_cast<int*>(bar_empty + kMaxStages);  // [4][4] = {n_pieces, base, nd, tile_end}
-    int* pc_so = rd + kMaxStages * 4;
-    int* pc_cnt = pc_so + NS * T;
-    int* p_lo = pc_cnt + NS * T;
-    int* p_hi = p_lo + T;
-    unsigned short* hot = reinterpret_cast<unsigned short*>(p_hi + T);
-    __shared__ int s_ncand, s_overflow, s_nhot;
-    __shared__ u64 s_theta;
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int q = blockIdx.x / a.splits;
-    const int sp = blockIdx.x - q * a.splits;
-    const int j0 = sp * a.tiles_per_split;
-    const int j1 = min(a.n_tiles, j0 + a.tiles_per_split);
-
-    for (int i = tid * 4; i < a.tile_docs; i += (NC + 32) * 4)
-        *reinterpret_cast<float4*>(sc + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid == 0) {
-        s_ncand = 0;
-        s_overflow = 0;
-        s_nhot = 0;
-        const u64 shared_theta = a.theta_q ? *reinterpret_cast<volatile u64*>(a.theta_q + q) : 0ull;
-        s_theta = shared_theta > a.theta0 ? shared_theta : a.theta0;
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(bar_full + s, 1);
-            mbar_init(bar_empty + s, NCW);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    if (warp == NCW) {
-        // =============================== producer warp ========================================
-        const int32_t* segq = a.seg + (int64_t)q * (a.n_tiles + 1) * T;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int t = lane; t < T; t += 32) p_hi[t] = __ldg(segq + (int64_t)j0 * T + t);
-        for (int j = j0; j < j1; ++j) {
-            for (int t = lane; t < T; t += 32) {
-                p_lo[t] = p_hi[t];
-                p_hi[t] = __ldg(segq + (int64_t)(j + 1) * T + t);
-            }
-            __syncwarp();
-            int t = 0;
-            while (t < T && p_hi[t] <= p_lo[t]) ++t;
-            if (t == T && !a.general) continue;  // no posting of this query in the tile
-            int pos = (t < T) ? p_lo[t] : 0;
-            const int base = j * a.tile_docs;
-            const int nd = min(a.tile_docs, a.n_docs - base);
-            do {  // one round = one staging buffer
-                mbar_wait(bar_empty + stage, phase ^ 1);
-                int used = 0, np = 0;
-                uint32_t bytes = 0;
-                while (t < T) {
-                    const int room = stg - used;
-                    if (room < 8) break;
-                    const int a0 = pos & ~3;  // bulk copies move whole 16-byte groups
-                    const int skip = pos - a0;
-                    const int take = min(p_hi[t] - pos, room - skip);
-                    const int ncopy = ((pos + take + 3) & ~3) - a0;
-                    if (lane == 0) {
-                        pc_so[stage * T + np] = stage * stg + used + skip;
-                        pc_cnt[stage * T + np] = take;
-                        bulk_copy_g2s(st_ids + stage * stg + used, a.ids + a0, (uint32_t)ncopy * 4u, bar_full + stage);
-                        bulk_copy_g2s(st_w + stage * stg + used, a.w + a0, (uint32_t)ncopy * 4u, bar_full + stage);
-                    }
-                    bytes += (uint32_t)ncopy * 8u;
-                    used += ncopy;
-                    ++np;
-                    pos += take;
-                    if (pos < p_hi[t]) break;  // buffer full, the term continues in the next round
-                    ++t;
-                    while (t < T && p_hi[t] <= p_lo[t]) ++t;
-                    if (t < T) pos = p_lo[t];
-                }
-                if (lane == 0) {
-                    rd[stage * 4 + 0] = np;
-                    rd[stage * 4 + 1] = base;
-                    rd[stage * 4 + 2] = nd;
-                    rd[stage * 4 + 3] = (t >= T) ? 1 : 0;
-                    mbar_arrive_expect_tx(bar_full + stage, bytes);
-                }
-                __syncwarp();
-                if (++stage == NS) { stage = 0; phase ^= 1; }
-            } while (t < T);
-        }
-        mbar_wait(bar_empty + stage, phase ^ 1);
-        if (lane == 0) {
-            rd[stage * 4 + 0] = -1;  // end of stream
-            mbar_arrive(bar_full + stage);
-        }
-        return;
-    }
-
-    // ================================= consumer warps =========================================
-    const WarpsGroup grp{NC, tid};
-    TopkState tk{cand, &s_ncand, &s_overflow, cap, 0ull, 0.f};
-    tk.set_theta(s_theta);
-    const bool use_hot = !a.general && !a.no_hot;
-    auto hot_add = [&](int slot) {
-        const int pos = atomicAdd(&s_nhot, 1);
-        if (pos < kHotCta) hot[pos] = (unsigned short)slot;
-    };
-    auto compact = [&]() {  // all consumer threads, no push in flight
-        compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
-        if (tid == 0) {
-            s_overflow = 0;
-            if (a.theta_q) {
-                const u64 mine = s_theta;
-                const u64 old = atomicMax(a.theta_q + q, mine);
-                if (old > mine) s_theta = old;
-            }
-        }
-        grp.sync();
-        tk.set_theta(s_theta);
-    };
-
-    int stage = 0;
-    uint32_t phase = 0;
-    for (;;) {
-        mbar_wait(bar_full + stage, phase);
-        const int np = rd[stage * 4 + 0];
-        if (np < 0) break;
-        const int base = rd[stage * 4 + 1];
-        const int nd = rd[stage * 4 + 2];
-        const int tile_end = rd[stage * 4 + 3];
-        // ---- accumulate the round's pieces: terms strictly in query order ---------------------
-        int i = 0;
-        while (i < np) {
-            const int cnt = pc_cnt[stage * T + i];
-            if (cnt > kSmallPiece) {
-                const int so = pc_so[stage * T + i];
-                for (int e = so + tid; e < so + cnt; e += 4 * NC) {
-                    const int hi = so + cnt;
-                    const bool v1 = e + NC < hi, v2 = e + 2 * NC < hi, v3 = e + 3 * NC < hi;
-                    const int i0 = st_ids[e] - base;
-                    const int i1 = v1 ? st_ids[e + NC] - base : 0;
-                    const int i2 = v2 ? st_ids[e + 2 * NC] - base : 0;
-                    const int i3 = v3 ? st_ids[e + 3 * NC] - base : 0;
-                    const float w0 = st_w[e];
-                    const float w1 = v1 ? st_w[e + NC] : 0.f;
-                    const float w2 = v2 ? st_w[e + 2 * NC] : 0.f;
-                    const float w3 = v3 ? st_w[e + 3 * NC] : 0.f;
-                    // one term has at most one posting per document: the four slots are distinct
-                    const float n0 = sc[i0] + w0;
-                    const float n1 = v1 ? sc[i1] + w1 : 0.f;
-                    const float n2 = v2 ? sc[i2] + w2 : 0.f;
-                    const float n3 = v3 ? sc[i3] + w3 : 0.f;
-                    sc[i0] = n0;
-                    if (v1) sc[i1] = n1;
-                    if (v2) sc[i2] = n2;
-                    if (v3) sc[i3] = n3;
-                    if (use_hot) {
-                        if (n0 >= tk.theta_f) hot_add(i0);
-                        if (v1 && n1 >= tk.theta_f) hot_add(i1);
-                        if (v2 && n2 >= tk.theta_f) hot_add(i2);
-                        if (v3 && n3 >= tk.theta_f) hot_add(i3);
-                    }
-                }
-                grp.sync();
-                ++i;
-            } else {
-                // a run of small pieces: warp 0 adds them one after the other, one barrier for the run
-                int i2 = i + 1;
-                while (i2 < np && pc_cnt[stage * T + i2] <= kSmallPiece) ++i2;
-                if (warp == 0) {
-                    for (int ii = i; ii < i2; ++ii) {
-                        const int so = pc_so[stage * T + ii];
-                        const int c2 = pc_cnt[stage * T + ii];
-                        for (int e = lane; e < c2; e += 32) {
-                            const int x = st_ids[so + e] - base;
-                            const float nw = sc[x] + st_w[so + e];
-                            sc[x] = nw;
-                            if (use_hot && nw >= tk.theta_f) hot_add(x);
-                        }
-                        __syncwarp();
-                    }
-                }
-                grp.sync();
-                i = i2;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_empty + stage);  // staging buffer may be refilled
-        if (++stage == NS) { stage = 0; phase ^= 1; }
-        if (!tile_end) continue;
-
-        // ---- tile epilogue (the last barrier above made every add visible) --------------------
-        const int nh = ld_volatile(&s_nhot);
-        if (use_hot && nh <= kHotCta) {
-            for (;;) {
-                for (int h = tid; h < nh; h += NC) {
-                    const int x = hot[h];
-                    // a slot may be listed several times: whoever swaps the score out owns it
-                    const float v = __int_as_float(atomicExch(reinterpret_cast<int*>(sc + x), 0));
-                    if (v > 0.f && !tk.push(v, (uint32_t)(base + x))) sc[x] = v;  // buffer full: put it back
-                }
-                grp.sync();
-                if (!ld_volatile(&s_overflow)) break;
-                grp.sync();
-                compact();
-            }
-            for (int idx = tid * 4; idx < a.tile_docs; idx += NC * 4)
-                *reinterpret_cast<float4*>(sc + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-            // dense scan: read, test and zero every slot (hot list overflowed or disabled)
-            for (;;) {
-                for (int idx = tid * 4; idx < nd; idx += NC * 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(sc + idx);
-                    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= tk.theta_f) {
-                        const float vv[4] = {v.x, v.y, v.z, v.w};
-                        float zz[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            if (vv[e] >= tk.theta_f && idx + e < nd) {
-                                if (!tk.push(vv[e], (uint32_t)(base + idx + e))) zz[e] = vv[e];
-                            }
-                        }
-                        z = make_float4(zz[0], zz[1], zz[2], zz[3]);
-                    }
-                    *reinterpret_cast<float4*>(sc + idx) = z;
-                }
-                grp.sync();
-                if (!ld_volatile(&s_overflow)) break;
-                grp.sync();
-                compact();
-            }
-        }
-        if (tid == 0) s_nhot = 0;
-        grp.sync();
-    }
-
-    grp.sync();
-    compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
-    if (tid == 0 && a.theta_q && s_ncand >= a.k) atomicMax(a.theta_q + q, s_theta);
-    const int n = s_ncand;
-    u64* out = a.partial + ((int64_t)q * a.splits + sp) * a.k;
-    for (int i = tid; i < a.k; i += NC) out[i] = (i < n) ? cand[i] : 0ull;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -266,11 +266,9 @@ def test_every_launch_shape_gives_identical_results(engine, workload, scale, k):
         dict(cap=k + 64), dict(cap=k + 64, consumer_warps=4, tile_docs=512), dict(no_hot=1), dict(no_priming=1),
         dict(no_priming=1, cap=k + 64, splits=1), dict(no_theta_share=1, splits=5), dict(consumer_warps=16, tile_docs=1024),
         dict(consumer_warps=12, tile_docs=4096, splits=2), dict(consumer_warps=1, tile_docs=128, splits=3),
-        dict(waves=1), dict(waves=20, no_hot=1, no_priming=1), dict(kernel=2), dict(kernel=2, cap=k + 64, cta_tile_docs=2048, stage_postings=256),
-        dict(kernel=2, no_hot=1, splits=3, stages=3), dict(kernel=2, no_priming=1, cta_tile_docs=1024, stage_postings=64, stages=4),
+        dict(waves=1), dict(waves=20, no_hot=1, no_priming=1),
     ]
-    names = ["cap", "consumer_warps", "tile_docs", "no_hot", "no_priming", "no_theta_share", "splits", "waves", "kernel",
-             "cta_tile_docs", "stage_postings", "stages"]
+    names = ["cap", "consumer_warps", "tile_docs", "no_hot", "no_priming", "no_theta_share", "splits", "waves"]
     for v in variants:
         for n in names:
             index.set_option(n, v.get(n, 0))
