@@ -299,3 +299,33 @@ def test_degenerate_shapes(engine):
     q[:, ::7] = rng.integers(0, 40, size=(5, 29))
     _check_batch(index, m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data, 700, q, 700)
     _check_batch(index, m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data, 700, q, 3)
+
+
+def test_fuzz_random_indices_and_knobs(engine):
+    """Seeded fuzz: random CSC shapes/densities (incl. heavy 'stop word' columns, empty columns,
+    documents no term touches), random ragged queries with padding and duplicates, random k and
+    random launch shapes -- ids and score bits must match the oracle every time."""
+    rng = np.random.default_rng(20260118)
+    for trial in range(40):
+        n_docs = int(rng.choice([1, 2, 37, 500, 2049, 7000, 30000]))
+        n_terms = int(rng.integers(1, 60))
+        cols, ptr = [], [0]
+        for t in range(n_terms):
+            mode = rng.integers(0, 4)
+            dens = [0.0, 0.002, 0.05, 0.9][mode]
+            rows = np.flatnonzero(rng.random(n_docs) < dens).astype(np.int32)
+            cols.append(rows)
+            ptr.append(ptr[-1] + len(rows))
+        indices = np.concatenate(cols) if ptr[-1] else np.zeros(0, np.int32)
+        data = (0.01 + rng.random(ptr[-1]) * rng.choice([1.0, 8.0])).astype(np.float32)
+        indptr = np.array(ptr, np.int32)
+        index = engine.DeviceIndex(indptr, indices, data, n_docs=n_docs)
+        n_q, width = int(rng.integers(1, 9)), int(rng.integers(1, 12))
+        q = rng.integers(-1, n_terms, size=(n_q, width)).astype(np.int32)
+        k = int(min(n_docs, rng.choice([1, 3, 10, 100, 1000])))
+        for name, choices in [("tile_docs", [0, 128, 512, 4096]), ("consumer_warps", [0, 1, 3, 8, 16]),
+                              ("splits", [0, 1, 2, 9]), ("cap", [0, k + 64]), ("no_hot", [0, 1]),
+                              ("no_priming", [0, 1]), ("no_theta_share", [0, 1]), ("wide_min", [0, 1, 10000])]:
+            index.set_option(name, int(rng.choice(choices)))
+        _check_batch(index, indptr, indices, data, n_docs, q, k)
+        index.close()
