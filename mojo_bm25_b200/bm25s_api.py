@@ -53,6 +53,37 @@ class BM25:
             self._index.close()
         self._index = DeviceIndex(indptr, indices, data, int(num_docs), device=self.device)
 
+    def index(self, corpus_tokens, n_terms: Optional[int] = None) -> None:
+        """bm25s-shaped ``index`` (the reference calls it at bm25_test.py:19-20): build the CSC weight
+        matrix ON THE GPU from a tokenised corpus and pin it in HBM.  ``corpus_tokens``: a list of
+        documents, each a list of token strings (the vocabulary is assigned in order of first
+        appearance) or of term ids; or a bm25s ``Tokenized``-like object with ``.ids`` / ``.vocab``."""
+        import torch
+
+        from . import index_build
+
+        vocab = None
+        if hasattr(corpus_tokens, "ids") and hasattr(corpus_tokens, "vocab"):
+            vocab, corpus_tokens = dict(corpus_tokens.vocab), corpus_tokens.ids
+        docs = [list(d) for d in corpus_tokens]
+        if any(d and isinstance(d[0], str) for d in docs):
+            vocab = {}
+            docs = [[vocab.setdefault(t, len(vocab)) for t in d] for d in docs]
+        if n_terms is None:
+            n_terms = len(vocab) if vocab is not None else (max((max(d) for d in docs if d), default=-1) + 1)
+        flat, doc_ptr = index_build.flatten_corpus(docs)
+        variant = "bm25py" if self.method == "bm25py" else "lucene"
+        indptr, indices, data, _ = index_build.build_csc(flat, doc_ptr, n_terms, k1=self.k1, b=self.b, variant=variant,
+                                                         device=f"cuda:{self.device}")
+        torch.cuda.synchronize(self.device)
+        self.vocab_dict = dict(vocab) if vocab is not None else {}
+        self.corpus = None
+        self.scores = {"data": data.cpu().numpy(), "indices": indices.cpu().numpy(), "indptr": indptr.cpu().numpy(),
+                       "num_docs": len(docs)}
+        if self._index is not None:
+            self._index.close()
+        self._index = DeviceIndex.from_torch(indptr, indices, data, len(docs), borrow=True)
+
     def save(self, save_dir: str, corpus=None) -> None:
         if self.scores is None:
             raise ValueError("nothing to save: no index loaded")

@@ -1,0 +1,97 @@
+"""Index builder: the torch pipeline (run here on the CPU device, on
+CUDA under -m gpu) against its numpy restatement and against the dense drop-in's host ``fit``."""
+import numpy as np
+import pytest
+import torch
+
+from mojo_bm25_b200 import index_build
+
+FOX = ["the quick brown fox jumps over the lazy dog", "a quick brown dog outpaces a lazy fox",
+       "the lazy dog sleeps", "tall trees in the forest", "the forest has tall tall trees and a fox", ""]
+
+
+def _random_corpus(rng, n_docs, n_terms, mean_len):
+    lens = rng.poisson(mean_len, size=n_docs)
+    lens[rng.integers(0, n_docs)] = 0
+    zipf = 1.0 / np.arange(1, n_terms + 1)
+    return [rng.choice(n_terms, size=int(l), p=zipf / zipf.sum()).tolist() for l in lens]
+
+
+def _same(a, b):
+    for x, y in zip(a, b):
+        x = x.cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+        y = y.cpu().numpy() if isinstance(y, torch.Tensor) else np.asarray(y)
+        assert x.dtype == y.dtype and x.shape == y.shape
+        assert np.array_equal(x.view(np.uint32) if x.dtype == np.float32 else x, y.view(np.uint32) if y.dtype == np.float32 else y)
+
+
+@pytest.mark.parametrize("variant", ["lucene", "bm25py"])
+def test_builder_matches_numpy_bitwise_on_cpu(variant):
+    rng = np.random.default_rng(7)
+    for n_docs, n_terms, mean_len in [(1, 3, 4), (50, 20, 6), (400, 300, 30)]:
+        flat, ptr = index_build.flatten_corpus(_random_corpus(rng, n_docs, n_terms, mean_len))
+        got = index_build.build_csc(flat, ptr, n_terms, variant=variant, device="cpu")
+        want = index_build.build_csc_reference_numpy(flat, ptr, n_terms, variant=variant)
+        _same(got, want)
+        indptr, indices = want[0], want[1]
+        assert indptr[-1] == len(indices)
+        for t in range(n_terms):  # canonical CSC: rows strictly ascending inside every column
+            col = indices[indptr[t]:indptr[t + 1]]
+            assert np.all(col[1:] > col[:-1])
+
+
+def test_bm25py_variant_equals_the_dense_dropins_fit():
+    """bm25.py:30-121 semantics: vocabulary sorted, weights as in BM25.fit (host numpy)."""
+    docs = [d.lower().split() for d in FOX]
+    vocab = sorted({t for d in docs for t in d})
+    tid = {t: i for i, t in enumerate(vocab)}
+    flat, ptr = index_build.flatten_corpus([[tid[t] for t in d] for d in docs])
+    got = index_build.build_csc(flat, ptr, len(vocab), variant="bm25py", device="cpu")
+    # the same arithmetic as mojo_bm25_b200/bm25.py::BM25.fit, restated without a device
+    want = index_build.build_csc_reference_numpy(flat, ptr, len(vocab), variant="bm25py")
+    _same(got, want)
+    from oracle import bm25_oracle as orc
+
+    o = orc.OracleBM25()
+    o.fit(docs)
+    dense = np.zeros((len(docs), len(vocab)), dtype=np.float64)
+    indptr, indices, data = (x.numpy() for x in got[:3])
+    cols = np.repeat(np.arange(len(vocab)), np.diff(indptr))
+    dense[indices, cols] = data
+    np.testing.assert_allclose(dense, np.asarray(o.bm25_matrix), rtol=1e-6, atol=0)
+
+
+def test_empty_inputs():
+    out = index_build.build_csc(np.zeros(0, np.int32), np.zeros(1, np.int64), 5, device="cpu")
+    assert out[0].tolist() == [0] * 6 and out[1].numel() == 0
+    with pytest.raises(ValueError):
+        index_build.build_csc(np.array([7], np.int32), np.array([0, 1]), 5, device="cpu")
+
+
+@pytest.mark.gpu
+def test_builder_on_gpu_and_bm25s_shaped_index_roundtrip(tmp_path):
+    from mojo_bm25_b200.bm25s_api import BM25
+    from oracle import bm25_oracle as orc
+
+    rng = np.random.default_rng(11)
+    corpus = _random_corpus(rng, 3000, 500, 25)
+    flat, ptr = index_build.flatten_corpus(corpus)
+    got = index_build.build_csc(flat, ptr, 500, variant="lucene", device="cuda")
+    want = index_build.build_csc_reference_numpy(flat, ptr, 500, variant="lucene")
+    _same(got, want)
+    r = BM25()
+    r.index(corpus, n_terms=500)
+    q = rng.integers(0, 500, size=(16, 5)).astype(np.int32)
+    res = r.retrieve(q, k=10)
+    indptr, indices, data = want[0], want[1], want[2]
+    for i in range(len(q)):
+        dense = orc.scores_dense(indptr, indices, data, 3000, q[i])
+        orc.check_topk_against_dense(res.documents[i], res.scores[i], dense, 10, exact=True)
+    # string tokens: vocabulary by first appearance; save -> load -> same answers
+    docs = [d.lower().split() for d in FOX[:5]]
+    r2 = BM25()
+    r2.index(docs)
+    a = r2.retrieve([["lazy", "fox"]], k=3)
+    r2.save(str(tmp_path / "idx"))
+    b = BM25.load(str(tmp_path / "idx")).retrieve([["lazy", "fox"]], k=3)
+    assert np.array_equal(a.documents, b.documents) and np.array_equal(a.scores, b.scores)
