@@ -166,6 +166,79 @@ __device__ __forceinline__ void compact_candidates(u64* cand, int cap, int k, u6
     g.sync();
 }
 
+// Large candidate sets (k > 256): radix select instead of a full sort.  Finds the k-th largest of
+// the n > k distinct keys in cand[0..n) (most significant byte first, one 256-bin shared-memory
+// histogram per pass, stops as soon as the bucket holding the k-th key has a single member), then
+// moves the k keys >= that threshold -- unsorted -- through `scratch` (k keys of global memory owned
+// by this CTA) back to cand[0..k).  O(n) per pass instead of O(n log^2 n) compare-exchanges.
+// hist: 264 ints of shared memory.  Called by every thread of the group with no push in flight.
+template <typename G>
+__device__ __forceinline__ void select_candidates(u64* cand, int n, int k, u64* scratch, int* hist, int* s_ncand,
+                                                  u64* s_theta, bool copy_back, const G& g) {
+    const int lane = g.rank & 31;
+    u64 prefix = 0, known = 0;  // known = mask of the key bits fixed so far
+    int need = k;
+    int* ctl = hist + 256;  // {digit, need, bucket, keeper count}
+    if (g.rank == 0) ctl[3] = 0;  // ordered before its first use by the barriers of the passes
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = g.rank; i < 256; i += g.size) hist[i] = 0;
+        g.sync();
+        for (int i = g.rank; i < n; i += g.size) {
+            const u64 key = cand[i];
+            if ((key & known) == prefix) atomicAdd(&hist[(int)(key >> shift) & 255], 1);
+        }
+        g.sync();
+        if (g.rank < 32) {  // lane L owns bins 255-8L .. 248-8L (descending)
+            int c[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { c[j] = hist[255 - 8 * lane - j]; s += c[j]; }
+            int cum = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(kFull, cum, o);
+                if (lane >= o) cum += v;
+            }
+            const unsigned hit = __ballot_sync(kFull, cum >= need);
+            if (lane == __ffs(hit) - 1) {
+                int above = cum - s;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (above + c[j] >= need) {
+                        ctl[0] = 255 - 8 * lane - j;
+                        ctl[1] = need - above;
+                        ctl[2] = c[j];
+                        break;
+                    }
+                    above += c[j];
+                }
+            }
+        }
+        g.sync();
+        prefix |= (u64)ctl[0] << shift;
+        known |= 0xffull << shift;
+        need = ctl[1];
+        if (ctl[2] == 1) break;  // the k-th key is the only one left with this prefix
+    }
+    // the threshold itself, and the move of the keepers
+    u64 theta = 0;
+    for (int i = g.rank; i < n; i += g.size) {
+        const u64 key = cand[i];
+        if ((key & known) == prefix) theta = key;  // exactly one thread sees it (or all 64 bits are known)
+    }
+    if (theta) *s_theta = theta;
+    g.sync();
+    theta = *s_theta;
+    for (int i = g.rank; i < n; i += g.size) {
+        const u64 key = cand[i];
+        if (key >= theta) scratch[atomicAdd(&ctl[3], 1)] = key;
+    }
+    g.sync();
+    if (copy_back)
+        for (int i = g.rank; i < k; i += g.size) cand[i] = scratch[i];
+    if (g.rank == 0) *s_ncand = k;
+    g.sync();
+}
+
 struct SearchArgs {
     const int32_t* __restrict__ ids;      // [nnz]   doc ids, columns sorted ascending
     const float* __restrict__ w;          // [nnz]   weights
@@ -248,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_scores_dense(const SearchArgs a
 //   | uint16 hot[NCW][kHotCap]
 // ---------------------------------------------------------------------------------------------
 constexpr int kDocNone = 0x7fffffff;
+constexpr int kSelectMin = 1024;  // candidate sets larger than this are compacted by radix select
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
@@ -379,6 +453,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     unsigned short* st_hot = reinterpret_cast<unsigned short*>(st_nxt + NCW * T);
     __shared__ int s_ncand, s_overflow;
     __shared__ u64 s_theta;
+    __shared__ int s_hist[264];  // select_candidates scratch
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -405,10 +480,15 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     int left_nd = 0;
     HotList hl{st_hot + warp * kHotCap, kHotCap + 1, (1u << lane) - 1u};
 
+    u64* out = a.partial + ((int64_t)q * a.splits + sp) * a.k;  // this CTA's k output keys (also select scratch)
+
     // candidate-buffer overflow round: every warp of the CTA takes part
     auto overflow_round = [&]() {
         for (;;) {
-            compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
+            if (cap > kSelectMin)  // a round is only entered with a full buffer (n = cap > k)
+                select_candidates(cand, cap, a.k, out, s_hist, &s_ncand, &s_theta, true, grp);
+            else
+                compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
             if (tid == 0) {
                 s_overflow = 0;
                 if (a.theta_q) {  // share the threshold with the other CTAs of this query
@@ -582,10 +662,16 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
         if (!ld_volatile(&s_overflow)) break;
         overflow_round();
     }
+    const int n_end = min(ld_volatile(&s_ncand), cap);
+    if (n_end > kSelectMin && n_end > a.k) {
+        // the k keepers go straight to the output slot, unsorted (k_merge sorts what it loads)
+        select_candidates(cand, n_end, a.k, out, s_hist, &s_ncand, &s_theta, false, grp);
+        if (tid == 0 && a.theta_q) atomicMax(a.theta_q + q, s_theta);
+        return;
+    }
     compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
     if (tid == 0 && a.theta_q && s_ncand >= a.k) atomicMax(a.theta_q + q, s_theta);
     const int n = s_ncand;
-    u64* out = a.partial + ((int64_t)q * a.splits + sp) * a.k;
     for (int i = tid; i < a.k; i += blockDim.x) out[i] = (i < n) ? cand[i] : 0ull;
 }
 
