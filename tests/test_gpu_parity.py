@@ -305,7 +305,7 @@ def test_fuzz_random_indices_and_knobs(engine):
     """Seeded fuzz: random CSC shapes/densities (incl. heavy 'stop word' columns, empty columns,
     documents no term touches), random ragged queries with padding and duplicates, random k and
     random launch shapes -- ids and score bits must match the oracle every time."""
-    rng = np.random.default_rng(20260118)
+    rng = np.random.default_rng(int(os.environ.get("BM25_FUZZ_SEED", "20260118")))  # override to widen the fuzz
     for trial in range(40):
         n_docs = int(rng.choice([1, 2, 37, 500, 2049, 7000, 30000]))
         n_terms = int(rng.integers(1, 60))
