@@ -166,7 +166,7 @@ __device__ __forceinline__ void compact_candidates(u64* cand, int cap, int k, u6
     g.sync();
 }
 
-// Large candidate sets (k > 256): radix select instead of a full sort.  Finds the k-th largest of
+// Candidate sets above kSelectMin keys: radix select instead of a full sort.  Finds the k-th largest of
 // the n > k distinct keys in cand[0..n) (most significant byte first, one 256-bin shared-memory
 // histogram per pass, stops as soon as the bucket holding the k-th key has a single member), then
 // moves the k keys >= that threshold -- unsorted -- through `scratch` (k keys of global memory owned
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_scores_dense(const SearchArgs a
 //   | uint16 hot[NCW][kHotCap]
 // ---------------------------------------------------------------------------------------------
 constexpr int kDocNone = 0x7fffffff;
-constexpr int kSelectMin = 1024;  // candidate sets larger than this are compacted by radix select
+constexpr int kSelectMin = 256;  // candidate sets larger than this are compacted by radix select
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
