@@ -80,6 +80,7 @@ int bm25_index_get_info(const bm25_index* index, bm25_index_info* out);
  *   "waves"          target number of CTA waves when "splits" is automatic (default 10; 4 for k > 256)
  *   "cap"            candidate-buffer keys per CTA (default max(4k, 512) up to k = 1024, else 2k; power of two)
  *   "force_general"  1: treat the index as if it held non-positive weights (every doc competes)
+ *   "cand_smem"      1: keep the candidate buffer in shared memory also for k > 256
  *   "no_hot" / "no_priming" / "no_theta_share"   1: disable the hot-list epilogue / the load-time
  *                    threshold priming / the per-query threshold shared between CTAs (A/B switches)
  *   "timing"         1: record CUDA events around the three kernels of every search */

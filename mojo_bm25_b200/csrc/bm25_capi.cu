@@ -159,13 +159,13 @@ struct bm25_index {
     std::vector<int32_t> h_indptr;  // host copy for byte accounting / validation
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
-    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_wide_min = 0;
+    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_wide_min = 0, opt_cand_smem = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace
     std::mutex mu;
     DevBuf<int32_t> ws_seg;
-    DevBuf<u64> ws_partial, ws_theta;
+    DevBuf<u64> ws_partial, ws_theta, ws_cand;
     DevBuf<int32_t> ws_queries, ws_out_ids;
     DevBuf<float> ws_out_scores;
     PinnedBuf<int32_t> pin_queries, pin_out_ids;
@@ -185,7 +185,7 @@ struct bm25_index {
         int64_t b = 0;
         if (!borrowed) b += (n_terms + 1) * 4 + nnz * 8;
         if (d_bounds) b += n_terms * kBoundLevels * 4;
-        b += ws_seg.bytes() + ws_partial.bytes() + ws_theta.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
+        b += ws_seg.bytes() + ws_partial.bytes() + ws_theta.bytes() + ws_cand.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
              ws_out_scores.bytes();
         return b;
     }
@@ -273,13 +273,14 @@ int canonicalise_host(const int32_t* indptr, const int32_t* indices, const float
 struct LaunchPlan {
     int tile_docs, n_tiles, splits, tiles_per_split, cap, warps, general;
     int tiles_per_chunk, n_chunks;  // k_score_topk: a chunk = the tiles one warp walks
+    int cand_global;                // candidate buffers live in global memory (k > kSelectMin)
     int seg_docs, seg_rows;         // granularity / row count of the segment table
     size_t smem;
     u64 theta0;
 };
 
 // dynamic shared memory of k_score_topk (layout documented at the kernel)
-size_t score_smem(int tile_docs, int cap, int64_t T, int warps) {
+size_t score_smem(int tile_docs, int cap, int64_t T, int warps) {  // cap = 0: candidates in global memory
     return (size_t)warps * tile_docs * 4 + (size_t)cap * 8 + (size_t)warps * T * 12 + (size_t)warps * kHotCap * 2 + 128;
 }
 
@@ -321,10 +322,13 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
     lp->cap = ix->opt_cap > 0 ? next_pow2(ix->opt_cap)
                               : next_pow2(std::max((k <= 1024 ? 4 : 2) * (int64_t)k, (int64_t)512));
     if (lp->cap < k + 64) lp->cap = next_pow2((int64_t)k + 64);
+    // large k: the candidate buffer moves to global memory (see the kernel); it is then compacted by
+    // radix select only, which needs cap > kSelectMin
+    lp->cand_global = (k > kSelectMin && !ix->opt_cand_smem) ? 1 : 0;
     // shrink the CTA (fewer warps, then smaller tiles) until it fits into shared memory
     const size_t hard = ix->smem_optin - 1024;
     for (;;) {
-        lp->smem = score_smem(lp->tile_docs, lp->cap, T, lp->warps);
+        lp->smem = score_smem(lp->tile_docs, lp->cand_global ? 0 : lp->cap, T, lp->warps);
         if (lp->smem <= hard) break;
         if (lp->warps > 4) { lp->warps -= 1; continue; }
         if (lp->tile_docs > 512) { lp->tile_docs -= 128; continue; }
@@ -434,6 +438,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     if (rc) return rc;
     if ((rc = ix->ws_partial.reserve((size_t)Q * lp.splits * k))) return rc;
     if ((rc = ix->ws_theta.reserve((size_t)Q))) return rc;
+    if (lp.cand_global && (rc = ix->ws_cand.reserve((size_t)Q * lp.splits * lp.cap))) return rc;
     CU(cudaMemsetAsync(ix->ws_theta.p, 0, (size_t)Q * sizeof(u64), st));
     const bool timing = ix->opt_timing != 0;
     if (timing) {
@@ -451,6 +456,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.seg = ix->ws_seg.p;
     a.partial = ix->ws_partial.p;
     a.theta_q = ix->opt_no_theta_share ? nullptr : ix->ws_theta.p;
+    a.cand_global = lp.cand_global ? ix->ws_cand.p : nullptr;
     a.dense_out = nullptr;
     a.theta0 = lp.theta0;
     a.Q = (int)Q;
@@ -662,6 +668,7 @@ int bm25_index_destroy(bm25_index* ix) {
         ix->ws_seg.release();
         ix->ws_partial.release();
         ix->ws_theta.release();
+        ix->ws_cand.release();
         ix->ws_queries.release();
         ix->ws_out_ids.release();
         ix->ws_out_scores.release();
@@ -717,6 +724,8 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
     } else if (!strcmp(name, "wide_min")) {
         if (value < 0 || value > (1 << 20)) return fail(BM25_ERR_INVALID, "wide_min out of range");
         ix->opt_wide_min = (int)value;
+    } else if (!strcmp(name, "cand_smem")) {
+        ix->opt_cand_smem = value ? 1 : 0;
     } else if (!strcmp(name, "no_hot")) {
         ix->opt_no_hot = value ? 1 : 0;
     } else if (!strcmp(name, "force_general")) {

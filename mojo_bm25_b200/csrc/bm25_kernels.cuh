@@ -246,6 +246,7 @@ struct SearchArgs {
     const int32_t* __restrict__ seg;      // [Q,n_chunks+1,T]  (k_scores_dense: [Q,n_tiles+1,T])
     u64* __restrict__ partial;            // [Q,splits,k] sorted keys (0 = none)
     u64* theta_q;                         // [Q] best known k-th key per query (shared by its CTAs)
+    u64* cand_global;                     // [Q*splits, cap] candidate buffers in global memory (large k), or NULL
     float* __restrict__ dense_out;        // [Q,n_docs]  (k_scores_dense only)
     u64 theta0;                           // initial threshold: key must be > theta0 to compete
     int Q, T, k;
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_scores_dense(const SearchArgs a
 // raise the threshold, which is also published per query in global memory so that the other
 // CTAs of the query prune with it.
 // shared memory (dynamic):
-//   float score[NCW][S] | u64 cand[cap] | int pos[NCW][T] | int cend[NCW][T] | int nxt[NCW][T]
+//   float score[NCW][S] | u64 cand[cap] (unless in global memory) | int pos[NCW][T] | int cend[NCW][T] | int nxt[NCW][T]
 //   | uint16 hot[NCW][kHotCap]
 // ---------------------------------------------------------------------------------------------
 constexpr int kDocNone = 0x7fffffff;
@@ -446,8 +447,11 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     const int NCW = blockDim.x >> 5;
     const int T = a.T, S = a.tile_docs, cap = a.cap;
     float* sc = reinterpret_cast<float*>(smem_raw);
-    u64* cand = reinterpret_cast<u64*>(sc + (size_t)NCW * S);
-    int* st_pos = reinterpret_cast<int*>(cand + cap);
+    // candidate buffer: shared memory, or (large k) this CTA's slice of a global, L2-resident array --
+    // pushes are rare once the threshold has settled, and the freed shared memory buys a third CTA per SM
+    u64* cand_smem = reinterpret_cast<u64*>(sc + (size_t)NCW * S);
+    u64* cand = a.cand_global ? a.cand_global + (size_t)blockIdx.x * cap : cand_smem;
+    int* st_pos = reinterpret_cast<int*>(cand_smem + (a.cand_global ? 0 : cap));
     int* st_end = st_pos + NCW * T;
     int* st_nxt = st_end + NCW * T;
     unsigned short* st_hot = reinterpret_cast<unsigned short*>(st_nxt + NCW * T);
@@ -667,6 +671,11 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
         // the k keepers go straight to the output slot, unsorted (k_merge sorts what it loads)
         select_candidates(cand, n_end, a.k, out, s_hist, &s_ncand, &s_theta, false, grp);
         if (tid == 0 && a.theta_q) atomicMax(a.theta_q + q, s_theta);
+        return;
+    }
+    if (a.cand_global) {
+        // here n_end <= k (a larger set went through the select above): everything is a keeper, unsorted
+        for (int i = tid; i < a.k; i += blockDim.x) out[i] = (i < n_end) ? cand[i] : 0ull;
         return;
     }
     compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
