@@ -36,6 +36,7 @@ extern "C" {
 #define BM25_ERR_OOM 5         /* host or device allocation failed                   */
 
 #define BM25_MAX_K 6144 /* largest supported top-k */
+#define BM25_MAX_DOCS (0x7fffffffLL - 65536) /* largest n_docs of one handle (int32 tile arithmetic) */
 
 typedef struct bm25_index bm25_index; /* opaque; owns the HBM-resident CSC arrays + workspace */
 
@@ -56,16 +57,19 @@ typedef struct bm25_index_info {
 /* Index loader (replaces: nothing in the reference loads the on-disk bm25s CSC index
  * animal_index_bm25/{indptr,indices,data}.csc.index.npy -- bm25_test.py:35-42 only round-trips it
  * through third-party bm25s; BM25v.index, bm25_native.py:59-74, takes the same three arrays as a
- * scipy csc_matrix).  Copies the host CSC arrays into HBM as int32 indptr/indices + fp32 weights,
- * canonicalises columns (sorted by doc id, duplicates summed) and precomputes tiling metadata.
+ * scipy csc_matrix).  Canonicalises the columns (sorted by doc id, duplicates summed) and pins them
+ * in HBM re-bucketed for document-range tiles: int32 doc ids + fp32 weights in 16-byte aligned,
+ * padded posting lists, {start, end} per term, and -- built on the first search -- a per-(heavy
+ * term, document tile) first-posting table.
  *   indptr  [n_terms+1] int32, indices [nnz] int32 in [0,n_docs), data [nnz] fp32 (finite). */
 int bm25_index_create(const int32_t* h_indptr, const int32_t* h_indices, const float* h_data,
                       int64_t n_terms, int64_t n_docs, int64_t nnz, int device,
                       int64_t doc_id_base, bm25_index** out);
 
 /* Same, from arrays already resident on `device` (e.g. a synthetic index generated in HBM).
- * The arrays must already be canonical (each column strictly increasing in doc id); they are
- * copied unless `borrow` != 0, in which case the caller keeps them alive and unmodified. */
+ * The arrays must already be canonical (each column strictly increasing in doc id).  They are only
+ * read during this call: the index is always re-bucketed into library-owned memory (`borrow` is
+ * accepted for source compatibility and ignored). */
 int bm25_index_create_device(const int32_t* d_indptr, const int32_t* d_indices, const float* d_data,
                              int64_t n_terms, int64_t n_docs, int64_t nnz, int device,
                              int64_t doc_id_base, int borrow, bm25_index** out);
@@ -81,6 +85,9 @@ int bm25_index_get_info(const bm25_index* index, bm25_index_info* out);
  *   "cap"            candidate-buffer keys per CTA (default max(4k, 512) up to k = 1024, else 2k; power of two)
  *   "force_general"  1: treat the index as if it held non-positive weights (every doc competes)
  *   "cand_smem"      1: keep the candidate buffer in shared memory also for k > 256
+ *   "heavy_min"      a term gets a row in the tile table when df*16 >= heavy_min * n_tiles (default 32,
+ *                    i.e. two postings per document tile on average); lighter terms are walked by cursors
+ *   "poison"         1 (debug): fill workspace and shared memory with 0xff before every search
  *   "no_hot" / "no_priming" / "no_theta_share"   1: disable the hot-list epilogue / the load-time
  *                    threshold priming / the per-query threshold shared between CTAs (A/B switches)
  *   "timing"         1: record CUDA events around the three kernels of every search */

@@ -151,19 +151,29 @@ struct bm25_index {
     int device = 0;
     int sm_count = 148;
     int64_t n_terms = 0, n_docs = 0, nnz = 0, doc_id_base = 0;
-    bool all_positive = false, was_sorted = true, borrowed = false;
-    int32_t* d_indptr = nullptr;
-    int32_t* d_ids = nullptr;
-    float* d_w = nullptr;
+    bool all_positive = false, was_sorted = true;
+    // the re-bucketed index (layout documented in bm25_kernels.cuh)
+    int64_t nnz_padded = 0;
+    int2* d_tptr = nullptr;         // [n_terms] {start, end} of every term in the padded arrays
+    int32_t* d_ids = nullptr;       // [nnz_padded]
+    float* d_w = nullptr;           // [nnz_padded]
+    int32_t* d_term_row = nullptr;  // [n_terms] tile-table row or -1
+    int32_t* d_tab = nullptr;       // [n_heavy, tab_tiles + 1]
+    int64_t n_heavy = 0, tab_bytes = 0;
+    int tab_tile_docs = 0, tab_heavy_min = 0;  // what the table was built for (0 = not built)
     float* d_bounds = nullptr;  // [n_terms][kBoundLevels] per-term weight order statistics (threshold priming)
-    std::vector<int32_t> h_indptr;  // host copy for byte accounting / validation
+    std::vector<int32_t> h_indptr;  // host copy for byte accounting / heavy-term selection
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
-    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_wide_min = 0, opt_cand_smem = 0;
+    int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_heavy_min = 0, opt_cand_smem = 0;
+    int opt_poison = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
-    // workspace
+    // workspace: one per handle; searches on different streams are ordered through ws_done
     std::mutex mu;
+    cudaEvent_t ws_done = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
     DevBuf<int32_t> ws_seg;
     DevBuf<u64> ws_partial, ws_theta, ws_cand;
     DevBuf<int32_t> ws_queries, ws_out_ids;
@@ -182,8 +192,7 @@ struct bm25_index {
     }
     int n_tiles() const { return (int)std::max<int64_t>(1, (n_docs + tile_docs() - 1) / tile_docs()); }
     int64_t device_bytes() const {
-        int64_t b = 0;
-        if (!borrowed) b += (n_terms + 1) * 4 + nnz * 8;
+        int64_t b = n_terms * 12 + nnz_padded * 8 + tab_bytes;
         if (d_bounds) b += n_terms * kBoundLevels * 4;
         b += ws_seg.bytes() + ws_partial.bytes() + ws_theta.bytes() + ws_cand.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
              ws_out_scores.bytes();
@@ -193,22 +202,106 @@ struct bm25_index {
 
 namespace {
 
-int finish_create(bm25_index* ix, const cudaDeviceProp& prop) {
+// Builds the re-bucketed index from canonical CSC arrays resident on the device (h_indptr is the
+// host copy of the column pointers): padded posting arrays + {start, end} per term, then the
+// per-term weight order statistics.  The tile table is built lazily (ensure_table) because it
+// depends on the tile size.
+int finish_create(bm25_index* ix, const cudaDeviceProp& prop, const int32_t* d_indptr_raw, const int32_t* d_ids_raw,
+                  const float* d_w_raw) {
     ix->sm_count = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
     ix->smem_per_sm = prop.sharedMemPerMultiprocessor;
     CU(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
-    if (ix->all_positive && ix->n_terms > 0 && ix->nnz > 0) {
+    CU(cudaEventCreateWithFlags(&ix->ws_done, cudaEventDisableTiming));
+    const int64_t V = ix->n_terms;
+    std::vector<int2> tptr((size_t)std::max<int64_t>(V, 1));
+    int64_t pos = 0;
+    for (int64_t t = 0; t < V; ++t) {
+        const int64_t df = ix->h_indptr[t + 1] - ix->h_indptr[t];
+        tptr[t] = make_int2((int)pos, (int)(pos + df));
+        pos += (df + 3) & ~(int64_t)3;
+        if (pos > 0x7fffffffLL - 8)
+            return fail(BM25_ERR_UNSUPPORTED, "index too large for int32 posting offsets after padding (%lld)",
+                        (long long)pos);
+    }
+    ix->nnz_padded = pos;
+    if (cudaMalloc(&ix->d_tptr, (size_t)std::max<int64_t>(V, 1) * sizeof(int2)) != cudaSuccess ||
+        cudaMalloc(&ix->d_ids, (size_t)(pos + 4) * 4) != cudaSuccess ||
+        cudaMalloc(&ix->d_w, (size_t)(pos + 4) * 4) != cudaSuccess ||
+        cudaMalloc(&ix->d_term_row, (size_t)std::max<int64_t>(V, 1) * 4) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(BM25_ERR_OOM, "cudaMalloc of the index (%lld postings) failed", (long long)ix->nnz);
+    }
+    CU(cudaMemcpy(ix->d_tptr, tptr.data(), (size_t)V * sizeof(int2), cudaMemcpyHostToDevice));
+    if (V > 0 && pos > 0) {
+        const int grid = (int)std::min<int64_t>(V, (int64_t)ix->sm_count * 16);
+        k_relayout<<<grid, 128>>>(d_indptr_raw, d_ids_raw, d_w_raw, ix->d_tptr, (int)V, ix->d_ids, ix->d_w);
+        ++g_launches;
+        CU(cudaGetLastError());
+    }
+    if (ix->all_positive && V > 0 && ix->nnz > 0) {
         // threshold priming table (see k_term_bounds / k_segments)
-        if (cudaMalloc(&ix->d_bounds, (size_t)ix->n_terms * kBoundLevels * sizeof(float)) != cudaSuccess) {
+        if (cudaMalloc(&ix->d_bounds, (size_t)V * kBoundLevels * sizeof(float)) != cudaSuccess) {
             cudaGetLastError();
             return fail(BM25_ERR_OOM, "cudaMalloc of the term-bound table failed");
         }
-        k_term_bounds<<<(unsigned)ix->n_terms, 128>>>(ix->d_indptr, ix->d_w, (int)ix->n_terms, ix->d_bounds);
+        k_term_bounds<<<(unsigned)V, 128>>>(ix->d_tptr, ix->d_w, (int)V, ix->d_bounds);
         ++g_launches;
         CU(cudaGetLastError());
-        CU(cudaDeviceSynchronize());
     }
+    CU(cudaDeviceSynchronize());
+    return BM25_OK;
+}
+
+// The tile table for S = tile_docs documents per tile (built on first use, rebuilt when the tile
+// size or the heavy-term threshold changes).  heavy_min is in 1/16 postings per tile: a term is
+// heavy when df * 16 >= heavy_min * n_tiles.
+int ensure_table(bm25_index* ix, int S) {
+    int hm = ix->opt_heavy_min > 0 ? ix->opt_heavy_min : 32;
+    if (ix->tab_tile_docs == S && ix->tab_heavy_min == hm) return BM25_OK;
+    CU(cudaDeviceSynchronize());  // no search may still be reading the old table
+    const int64_t V = ix->n_terms;
+    const int64_t NB = std::max<int64_t>(1, (ix->n_docs + S - 1) / S);
+    std::vector<int32_t> row((size_t)std::max<int64_t>(V, 1), -1), heavy;
+    const int64_t limit = std::max<int64_t>(4 * ix->nnz, (int64_t)1 << 22);  // table entries
+    int eff = hm;
+    for (;;) {
+        heavy.clear();
+        for (int64_t t = 0; t < V; ++t) {
+            const int64_t df = ix->h_indptr[t + 1] - ix->h_indptr[t];
+            if (df > 0 && df * 16 >= (int64_t)eff * NB) heavy.push_back((int32_t)t);
+        }
+        if ((int64_t)heavy.size() * (NB + 1) <= limit || eff > (1 << 28)) break;
+        eff *= 2;
+    }
+    for (size_t r = 0; r < heavy.size(); ++r) row[heavy[r]] = (int32_t)r;
+    if (ix->d_tab) cudaFree(ix->d_tab);
+    ix->d_tab = nullptr;
+    ix->tab_bytes = 0;
+    ix->tab_tile_docs = 0;
+    const int64_t entries = (int64_t)heavy.size() * (NB + 1);
+    if (V > 0) CU(cudaMemcpy(ix->d_term_row, row.data(), (size_t)V * 4, cudaMemcpyHostToDevice));
+    if (entries > 0) {
+        int32_t* d_heavy = nullptr;
+        if (cudaMalloc(&ix->d_tab, (size_t)entries * 4) != cudaSuccess ||
+            cudaMalloc(&d_heavy, heavy.size() * 4) != cudaSuccess) {
+            cudaGetLastError();
+            if (ix->d_tab) cudaFree(ix->d_tab);
+            ix->d_tab = nullptr;
+            return fail(BM25_ERR_OOM, "cudaMalloc of the tile table (%lld entries) failed", (long long)entries);
+        }
+        cudaMemcpy(d_heavy, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice);
+        k_build_table<<<(unsigned)((entries + 255) / 256), 256>>>(ix->d_tptr, d_heavy, ix->d_ids, entries, (int)NB, S,
+                                                                  ix->d_tab);
+        ++g_launches;
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaFree(d_heavy);
+        if (e != cudaSuccess) return fail(BM25_ERR_CUDA, "building the tile table failed: %s", cudaGetErrorString(e));
+    }
+    ix->n_heavy = (int64_t)heavy.size();
+    ix->tab_bytes = entries * 4;
+    ix->tab_tile_docs = S;
+    ix->tab_heavy_min = hm;
     return BM25_OK;
 }
 
@@ -281,7 +374,7 @@ struct LaunchPlan {
 
 // dynamic shared memory of k_score_topk (layout documented at the kernel)
 size_t score_smem(int tile_docs, int cap, int64_t T, int warps) {  // cap = 0: candidates in global memory
-    return (size_t)warps * tile_docs * 4 + (size_t)cap * 8 + (size_t)warps * T * 12 + (size_t)warps * kHotCap * 2 + 128;
+    return (size_t)warps * tile_docs * 4 + (size_t)cap * 8 + (size_t)warps * T * kStateInts * 4 + (size_t)warps * kHotCap * 2 + 128;
 }
 
 void plan_mode(const bm25_index* ix, LaunchPlan* lp) {
@@ -392,7 +485,7 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
 }
 
 int launch_segments(bm25_index* ix, const LaunchPlan& lp, const int32_t* d_queries, int64_t Q, int64_t T, int k,
-                    u64* theta_q, cudaStream_t st) {
+                    u64* theta_q, bool all_terms, cudaStream_t st) {
     const int64_t n_qt = Q * T;
     int rc = ix->ws_seg.reserve((size_t)n_qt * (lp.seg_rows + 1));
     if (rc) return rc;
@@ -401,8 +494,8 @@ int launch_segments(bm25_index* ix, const LaunchPlan& lp, const int32_t* d_queri
     while ((1 << level) < k) ++level;
     const bool prime = theta_q && ix->d_bounds && !lp.general && level < kBoundLevels && !ix->opt_no_priming;
     const int64_t blocks = (n_qt * 32 + 255) / 256;
-    k_segments<<<(unsigned)blocks, 256, 0, st>>>(ix->d_indptr, ix->d_ids, d_queries, n_qt, (int)T, (int)ix->n_terms,
-                                                 lp.seg_docs, lp.seg_rows, ix->ws_seg.p,
+    k_segments<<<(unsigned)blocks, 256, 0, st>>>(ix->d_tptr, all_terms ? nullptr : ix->d_term_row, ix->d_ids, d_queries,
+                                                 n_qt, (int)T, (int)ix->n_terms, lp.seg_docs, lp.seg_rows, ix->ws_seg.p,
                                                  prime ? ix->d_bounds : nullptr, level, theta_q);
     ++g_launches;
     CU(cudaGetLastError());
@@ -439,6 +532,15 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     if ((rc = ix->ws_partial.reserve((size_t)Q * lp.splits * k))) return rc;
     if ((rc = ix->ws_theta.reserve((size_t)Q))) return rc;
     if (lp.cand_global && (rc = ix->ws_cand.reserve((size_t)Q * lp.splits * lp.cap))) return rc;
+    if ((rc = ix->ws_seg.reserve((size_t)Q * T * (lp.seg_rows + 1)))) return rc;
+    if ((rc = ensure_table(ix, lp.tile_docs))) return rc;
+    // the workspace is per handle: a search on another stream waits for the previous one
+    if (ix->ws_used && ix->ws_stream != st) CU(cudaStreamWaitEvent(st, ix->ws_done, 0));
+    if (ix->opt_poison) {  // debug: uninitialised workspace reads must not pass by luck
+        CU(cudaMemsetAsync(ix->ws_seg.p, 0xff, ix->ws_seg.bytes(), st));
+        CU(cudaMemsetAsync(ix->ws_partial.p, 0xff, ix->ws_partial.bytes(), st));
+        if (ix->ws_cand.p) CU(cudaMemsetAsync(ix->ws_cand.p, 0xff, ix->ws_cand.bytes(), st));
+    }
     CU(cudaMemsetAsync(ix->ws_theta.p, 0, (size_t)Q * sizeof(u64), st));
     const bool timing = ix->opt_timing != 0;
     if (timing) {
@@ -447,11 +549,13 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
         ix->ev_valid = false;
         CU(cudaEventRecord(ix->ev[0], st));
     }
-    if ((rc = launch_segments(ix, lp, d_queries, Q, T, k, ix->opt_no_theta_share ? nullptr : ix->ws_theta.p, st))) return rc;
+    if ((rc = launch_segments(ix, lp, d_queries, Q, T, k, ix->opt_no_theta_share ? nullptr : ix->ws_theta.p, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[1], st));
     SearchArgs a{};
     a.ids = ix->d_ids;
     a.w = ix->d_w;
+    a.term_row = ix->d_term_row;
+    a.tab = ix->d_tab;
     a.queries = d_queries;
     a.seg = ix->ws_seg.p;
     a.partial = ix->ws_partial.p;
@@ -462,6 +566,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.Q = (int)Q;
     a.T = (int)T;
     a.k = k;
+    a.n_terms = (int)ix->n_terms;
     a.n_docs = (int)ix->n_docs;
     a.tile_docs = lp.tile_docs;
     a.n_tiles = lp.n_tiles;
@@ -472,7 +577,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.cap = lp.cap;
     a.general = lp.general;
     a.no_hot = ix->opt_no_hot;
-    a.wide_min = ix->opt_wide_min > 0 ? ix->opt_wide_min : 64;
+    a.poison = ix->opt_poison;
     if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
     MergeArgs m{};
@@ -491,6 +596,9 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
         CU(cudaEventRecord(ix->ev[3], st));
         ix->ev_valid = true;
     }
+    CU(cudaEventRecord(ix->ws_done, st));
+    ix->ws_stream = st;
+    ix->ws_used = true;
     return BM25_OK;
 }
 
@@ -518,7 +626,7 @@ int bm25_index_create(const int32_t* h_indptr, const int32_t* h_indices, const f
     if (!out) return fail(BM25_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (!h_indptr || (nnz > 0 && (!h_indices || !h_data))) return fail(BM25_ERR_INVALID, "NULL index array");
-    if (n_terms < 0 || n_docs < 0 || nnz < 0 || nnz > 0x7fffffffLL || n_docs > 0x7fffffffLL)
+    if (n_terms < 0 || n_docs < 0 || nnz < 0 || nnz > 0x7fffffffLL || n_docs > BM25_MAX_DOCS)
         return fail(BM25_ERR_INVALID, "bad index shape (terms=%lld docs=%lld nnz=%lld)", (long long)n_terms,
                     (long long)n_docs, (long long)nnz);
     if (n_docs + doc_id_base > 0x7fffffffLL)
@@ -554,22 +662,32 @@ int bm25_index_create(const int32_t* h_indptr, const int32_t* h_indices, const f
         bm25_index_destroy(ix);
         return code;
     };
-    // +64 elements of slack so that vectorised kernels may over-read past the last posting
-    if (cudaMalloc(&ix->d_indptr, (n_terms + 1 + 64) * 4) != cudaSuccess ||
-        cudaMalloc(&ix->d_ids, (nnz + 64) * 4) != cudaSuccess ||
-        cudaMalloc(&ix->d_w, (nnz + 64) * 4) != cudaSuccess) {
+    // raw CSC arrays go to the device only as the source of the re-bucketing copy
+    int32_t *raw_ptr = nullptr, *raw_ids = nullptr;
+    float* raw_w = nullptr;
+    auto free_raw = [&]() {
+        if (raw_ptr) cudaFree(raw_ptr);
+        if (raw_ids) cudaFree(raw_ids);
+        if (raw_w) cudaFree(raw_w);
+    };
+    if (cudaMalloc(&raw_ptr, (size_t)(n_terms + 1) * 4) != cudaSuccess ||
+        cudaMalloc(&raw_ids, (size_t)std::max<int64_t>(nnz, 1) * 4) != cudaSuccess ||
+        cudaMalloc(&raw_w, (size_t)std::max<int64_t>(nnz, 1) * 4) != cudaSuccess) {
         cudaGetLastError();
+        free_raw();
         return cleanup(fail(BM25_ERR_OOM, "cudaMalloc of the index (%lld postings) failed", (long long)nnz));
     }
-    if (cudaMemset(ix->d_ids + nnz, 0x7f, 64 * 4) != cudaSuccess || cudaMemset(ix->d_w + nnz, 0, 64 * 4) != cudaSuccess ||
-        cudaMemcpy(ix->d_indptr, h_indptr, (n_terms + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-        (nnz > 0 && (cudaMemcpy(ix->d_ids, h_indices, nnz * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-                     cudaMemcpy(ix->d_w, h_data, nnz * 4, cudaMemcpyHostToDevice) != cudaSuccess))) {
+    if (cudaMemcpy(raw_ptr, h_indptr, (size_t)(n_terms + 1) * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+        (nnz > 0 && (cudaMemcpy(raw_ids, h_indices, (size_t)nnz * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+                     cudaMemcpy(raw_w, h_data, (size_t)nnz * 4, cudaMemcpyHostToDevice) != cudaSuccess))) {
         cudaError_t e = cudaGetLastError();
+        free_raw();
         return cleanup(fail(BM25_ERR_CUDA, "copying the index to device %d failed: %s", device,
                             cudaGetErrorString(e)));
     }
-    if ((rc = finish_create(ix, prop))) return cleanup(rc);
+    rc = finish_create(ix, prop, raw_ptr, raw_ids, raw_w);
+    free_raw();
+    if (rc) return cleanup(rc);
     *out = ix;
     return BM25_OK;
 }
@@ -580,7 +698,7 @@ int bm25_index_create_device(const int32_t* d_indptr, const int32_t* d_indices, 
     if (!out) return fail(BM25_ERR_INVALID, "out is NULL");
     *out = nullptr;
     if (!d_indptr || (nnz > 0 && (!d_indices || !d_data))) return fail(BM25_ERR_INVALID, "NULL index array");
-    if (n_terms < 0 || n_docs < 0 || nnz < 0 || nnz > 0x7fffffffLL || n_docs > 0x7fffffffLL)
+    if (n_terms < 0 || n_docs < 0 || nnz < 0 || nnz > 0x7fffffffLL || n_docs > BM25_MAX_DOCS)
         return fail(BM25_ERR_INVALID, "bad index shape (terms=%lld docs=%lld nnz=%lld)", (long long)n_terms,
                     (long long)n_docs, (long long)nnz);
     if (n_docs + doc_id_base > 0x7fffffffLL)
@@ -630,27 +748,10 @@ int bm25_index_create_device(const int32_t* d_indptr, const int32_t* d_indices, 
     };
     if (cudaMemcpy(ix->h_indptr.data(), d_indptr, (n_terms + 1) * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
         return cleanup(fail(BM25_ERR_CUDA, "reading indptr back failed"));
-    if (borrow) {
-        ix->borrowed = true;
-        ix->d_indptr = const_cast<int32_t*>(d_indptr);
-        ix->d_ids = const_cast<int32_t*>(d_indices);
-        ix->d_w = const_cast<float*>(d_data);
-    } else {
-        if (cudaMalloc(&ix->d_indptr, (n_terms + 1 + 64) * 4) != cudaSuccess ||
-            cudaMalloc(&ix->d_ids, (nnz + 64) * 4) != cudaSuccess ||
-            cudaMalloc(&ix->d_w, (nnz + 64) * 4) != cudaSuccess) {
-            cudaGetLastError();
-            return cleanup(fail(BM25_ERR_OOM, "cudaMalloc of the index (%lld postings) failed", (long long)nnz));
-        }
-        if (cudaMemset(ix->d_ids + nnz, 0x7f, 64 * 4) != cudaSuccess ||
-            cudaMemset(ix->d_w + nnz, 0, 64 * 4) != cudaSuccess ||
-            cudaMemcpy(ix->d_indptr, d_indptr, (n_terms + 1) * 4, cudaMemcpyDeviceToDevice) != cudaSuccess ||
-            (nnz > 0 && (cudaMemcpy(ix->d_ids, d_indices, nnz * 4, cudaMemcpyDeviceToDevice) != cudaSuccess ||
-                         cudaMemcpy(ix->d_w, d_data, nnz * 4, cudaMemcpyDeviceToDevice) != cudaSuccess)))
-            return cleanup(fail(BM25_ERR_CUDA, "device copy of the index failed: %s",
-                                cudaGetErrorString(cudaGetLastError())));
-    }
-    if ((rc = finish_create(ix, prop))) return cleanup(rc);
+    // `borrow` is accepted for source compatibility: the index is always re-bucketed into
+    // library-owned memory, the caller's arrays are only read during this call
+    (void)borrow;
+    if ((rc = finish_create(ix, prop, d_indptr, d_indices, d_data))) return cleanup(rc);
     *out = ix;
     return BM25_OK;
 }
@@ -659,12 +760,13 @@ int bm25_index_destroy(bm25_index* ix) {
     if (!ix) return BM25_OK;
     {
         DeviceGuard g(ix->device);
-        if (!ix->borrowed) {
-            if (ix->d_indptr) cudaFree(ix->d_indptr);
-            if (ix->d_ids) cudaFree(ix->d_ids);
-            if (ix->d_w) cudaFree(ix->d_w);
-        }
+        if (ix->d_tptr) cudaFree(ix->d_tptr);
+        if (ix->d_ids) cudaFree(ix->d_ids);
+        if (ix->d_w) cudaFree(ix->d_w);
+        if (ix->d_term_row) cudaFree(ix->d_term_row);
+        if (ix->d_tab) cudaFree(ix->d_tab);
         if (ix->d_bounds) cudaFree(ix->d_bounds);
+        if (ix->ws_done) cudaEventDestroy(ix->ws_done);
         ix->ws_seg.release();
         ix->ws_partial.release();
         ix->ws_theta.release();
@@ -721,9 +823,11 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
         ix->opt_no_theta_share = value ? 1 : 0;
     } else if (!strcmp(name, "no_priming")) {
         ix->opt_no_priming = value ? 1 : 0;
-    } else if (!strcmp(name, "wide_min")) {
-        if (value < 0 || value > (1 << 20)) return fail(BM25_ERR_INVALID, "wide_min out of range");
-        ix->opt_wide_min = (int)value;
+    } else if (!strcmp(name, "heavy_min")) {
+        if (value < 0 || value > (1 << 28)) return fail(BM25_ERR_INVALID, "heavy_min out of range");
+        ix->opt_heavy_min = (int)value;
+    } else if (!strcmp(name, "poison")) {
+        ix->opt_poison = value ? 1 : 0;
     } else if (!strcmp(name, "cand_smem")) {
         ix->opt_cand_smem = value ? 1 : 0;
     } else if (!strcmp(name, "no_hot")) {
@@ -804,7 +908,8 @@ int bm25_scores_dense(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64
     LaunchPlan lp;
     int rc = make_plan_dense(ix, Q, T, &lp);
     if (rc) return rc;
-    if ((rc = launch_segments(ix, lp, d_queries, Q, T, 1, nullptr, st))) return rc;
+    if (ix->ws_used && ix->ws_stream != st) CU(cudaStreamWaitEvent(st, ix->ws_done, 0));
+    if ((rc = launch_segments(ix, lp, d_queries, Q, T, 1, nullptr, true, st))) return rc;
     SearchArgs a{};
     a.ids = ix->d_ids;
     a.w = ix->d_w;
@@ -820,7 +925,11 @@ int bm25_scores_dense(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64
     a.splits = lp.splits;
     a.tiles_per_split = lp.tiles_per_split;
     a.cap = 0;
-    return launch_score(ix, lp, a, Q, true, st);
+    if ((rc = launch_score(ix, lp, a, Q, true, st))) return rc;
+    CU(cudaEventRecord(ix->ws_done, st));
+    ix->ws_stream = st;
+    ix->ws_used = true;
+    return BM25_OK;
 }
 
 int bm25_scores_dense_host(bm25_index* ix, const int32_t* h_queries, int64_t Q, int64_t T, float* h_out) {

@@ -6,11 +6,15 @@
 // and select the top-k by (score desc, doc id asc).
 //
 // Kernels:
-//   k_segments      per (query, term): posting-index boundaries of every document chunk
-//                   (binary search on doc id inside the term's posting slice)
+//   k_relayout      load time: CSC postings -> padded, 16-byte aligned posting lists
+//   k_build_table   load time: per (heavy term, document tile) first-posting table
+//   k_term_bounds   load time: per-term weight order statistics (threshold priming)
+//   k_segments      per (query, term): threshold priming; cursor starts of the light terms for
+//                   every document chunk (binary search on doc id inside the term's posting list)
 //   k_score_topk    one warp per (query, document chunk): private shared-memory score tile,
-//                   in-order accumulation from per-term cursors, fused threshold-pruned scan
-//                   into the CTA's candidate buffer; emits k sorted 64-bit keys per (query, CTA)
+//                   in-order accumulation (heavy terms: table-addressed 16-byte vector loads;
+//                   light terms: cursors with cp.async-prefetched heads), fused threshold-pruned
+//                   top-k into the CTA's candidate buffer; emits k 64-bit keys per (query, CTA)
 //   k_merge         per query: merge candidate lists (tile ranges or GPU shards), zero-score
 //                   fill, unpack to (doc id, score)
 //   k_validate_*    load-time canonical-form checks of the CSC arrays
@@ -54,16 +58,78 @@ __host__ __device__ __forceinline__ u64 make_key(float score, uint32_t doc) {
 __host__ __device__ __forceinline__ uint32_t key_doc(u64 key) { return 0xffffffffu - (uint32_t)key; }
 __host__ __device__ __forceinline__ float key_score(u64 key) { return ord_to_f32((uint32_t)(key >> 32)); }
 
+constexpr int kDocNone = 0x7fffffff;  // sentinel doc id: padding postings, exhausted cursors
+constexpr int kSelectMin = 256;       // candidate sets larger than this are compacted by radix select
+constexpr int kStateInts = 8;         // ints of cursor state per (warp, query term) in k_score_topk
+
 // ---------------------------------------------------------------------------------------------
-// k_segments: seg[(q*(n_tiles+1) + j)*T + t] = first posting index of term queries[q,t] whose doc
-// id is >= j*tile_docs (absolute index into ids/w); row n_tiles is the end of the slice.
-// Tile-major so that one tile's T boundaries are contiguous.  One warp per (query, term); lanes
-// stride over tile boundaries (binary search on doc id inside the term's posting slice).
+// The index in HBM ("re-bucketed into document-range tiles", built at load time):
+//   ids / w     posting arrays in the PADDED layout: every term's posting list starts at a multiple
+//               of 4 elements (16 bytes) and is padded at the end with (kDocNone, 0.0) postings up
+//               to the next multiple of 4, so that 16-byte vector loads never straddle two terms.
+//   tptr[t]     {start, end} of term t's list in the padded arrays (end - start = df_t).
+//   term_row[t] row of term t in the tile table, or -1.  "Heavy" terms (df_t >= heavy_min postings
+//               per document tile on average) own a row; "light" terms are walked with cursors.
+//   tab[r][j]   for heavy row r and tile j in [0, n_tiles]: index (padded layout) of the first
+//               posting whose doc id is >= j * tile_docs.  Tile j's postings of that term are
+//               [tab[r][j], tab[r][j+1]) -- known WITHOUT looking at any doc id, so the score
+//               kernel's loads never depend on previously loaded postings.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_segments(const int32_t* __restrict__ indptr,
+
+// k_relayout (load time): copy CSC postings into the padded layout.  One CTA per term (grid-stride).
+__global__ void __launch_bounds__(128) k_relayout(const int32_t* __restrict__ indptr, const int32_t* __restrict__ ids_in,
+                                                  const float* __restrict__ w_in, const int2* __restrict__ tptr,
+                                                  int n_terms, int32_t* __restrict__ ids_out,
+                                                  float* __restrict__ w_out) {
+    for (int t = blockIdx.x; t < n_terms; t += gridDim.x) {
+        const int s = indptr[t];
+        const int n = indptr[t + 1] - s;
+        const int o = tptr[t].x;
+        const int padded = (n + 3) & ~3;
+        for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+            ids_out[o + i] = i < n ? ids_in[s + i] : kDocNone;
+            w_out[o + i] = i < n ? w_in[s + i] : 0.f;
+        }
+    }
+}
+
+// k_build_table (load time / when tile_docs changes): tab[r][j] by binary search on doc id.
+__global__ void __launch_bounds__(256) k_build_table(const int2* __restrict__ tptr,
+                                                     const int32_t* __restrict__ heavy_terms,
+                                                     const int32_t* __restrict__ ids, int64_t n_entries,
+                                                     int n_tiles, int tile_docs, int32_t* __restrict__ tab) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_entries) return;
+    const int64_t row = i / (n_tiles + 1);
+    const int j = (int)(i - row * (n_tiles + 1));
+    const int2 se = tptr[heavy_terms[row]];
+    int lo = se.x, hi = se.y;
+    if (j == 0) hi = lo;
+    else if (j == n_tiles) lo = hi;
+    else {
+        const int64_t target = (int64_t)j * tile_docs;
+        while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if ((int64_t)__ldg(ids + mid) < target) lo = mid + 1; else hi = mid;
+        }
+    }
+    tab[i] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_segments: per (query, term) one warp.
+//  * threshold priming (lane 0): theta_q[q] = max over the query's terms of the 2^level-th largest
+//    weight of the term (see k_term_bounds).
+//  * cursor starts: seg[(q*(n_rows+1) + c)*T + t] = first posting index of term queries[q,t] whose
+//    doc id is >= c*row_docs (index into the padded ids/w); row n_rows is the end of the list.
+//    Row-major so that one row's T boundaries are contiguous.  Lanes stride over the rows (binary
+//    search on doc id inside the term's list).  Terms with a row in the tile table are skipped
+//    when `term_row` is given: the score kernel never reads their cursor starts.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_segments(const int2* __restrict__ tptr, const int32_t* __restrict__ term_row,
                                                   const int32_t* __restrict__ ids,
                                                   const int32_t* __restrict__ queries, int64_t n_qt,
-                                                  int T, int n_terms, int tile_docs, int n_tiles,
+                                                  int T, int n_terms, int row_docs, int n_rows,
                                                   int32_t* __restrict__ seg,
                                                   const float* __restrict__ bounds, int level,
                                                   u64* __restrict__ theta_q) {
@@ -74,7 +140,13 @@ __global__ void __launch_bounds__(256) k_segments(const int32_t* __restrict__ in
     const int64_t q = warp / T;
     const int t = (int)(warp - q * T);
     int lo0 = 0, hi0 = 0;
-    if (term >= 0 && term < n_terms) { lo0 = indptr[term]; hi0 = indptr[term + 1]; }
+    bool heavy = false;
+    if (term >= 0 && term < n_terms) {
+        const int2 se = tptr[term];
+        lo0 = se.x;
+        hi0 = se.y;
+        heavy = term_row != nullptr && term_row[term] >= 0;
+    }
     // threshold priming: the 2^level-th largest weight of this term belongs to 2^level distinct
     // documents whose score is at least that weight (all weights > 0), so it bounds the k-th best
     // score of the query from below for every k <= 2^level.
@@ -82,13 +154,14 @@ __global__ void __launch_bounds__(256) k_segments(const int32_t* __restrict__ in
         const float b = __ldg(bounds + (int64_t)term * kBoundLevels + level);
         if (b > 0.f) atomicMax(theta_q + q, make_key(b, 0xffffffffu) - 1ull);
     }
-    int32_t* out = seg + q * (int64_t)(n_tiles + 1) * T + t;
-    for (int j = lane; j <= n_tiles; j += 32) {
+    if (heavy) return;
+    int32_t* out = seg + q * (int64_t)(n_rows + 1) * T + t;
+    for (int j = lane; j <= n_rows; j += 32) {
         int res;
         if (j == 0) res = lo0;
-        else if (j == n_tiles) res = hi0;
+        else if (j == n_rows) res = hi0;
         else {
-            const int64_t target = (int64_t)j * tile_docs;
+            const int64_t target = (int64_t)j * row_docs;
             int lo = lo0, hi = hi0;
             while (lo < hi) {
                 const int mid = lo + ((hi - lo) >> 1);
@@ -240,22 +313,25 @@ __device__ __forceinline__ void select_candidates(u64* cand, int n, int k, u64* 
 }
 
 struct SearchArgs {
-    const int32_t* __restrict__ ids;      // [nnz]   doc ids, columns sorted ascending
-    const float* __restrict__ w;          // [nnz]   weights
-    const int32_t* __restrict__ queries;  // [Q,T]
-    const int32_t* __restrict__ seg;      // [Q,n_chunks+1,T]  (k_scores_dense: [Q,n_tiles+1,T])
-    u64* __restrict__ partial;            // [Q,splits,k] sorted keys (0 = none)
-    u64* theta_q;                         // [Q] best known k-th key per query (shared by its CTAs)
-    u64* cand_global;                     // [Q*splits, cap] candidate buffers in global memory (large k), or NULL
-    float* __restrict__ dense_out;        // [Q,n_docs]  (k_scores_dense only)
-    u64 theta0;                           // initial threshold: key must be > theta0 to compete
+    const int32_t* __restrict__ ids;       // [nnz_padded] doc ids (padded layout, see above)
+    const float* __restrict__ w;           // [nnz_padded] weights
+    const int32_t* __restrict__ term_row;  // [V] tile-table row of a heavy term, -1 for a light term
+    const int32_t* __restrict__ tab;       // [n_heavy, n_tiles+1] tile table
+    const int32_t* __restrict__ queries;   // [Q,T]
+    const int32_t* __restrict__ seg;       // [Q,n_chunks+1,T] cursor starts of the light terms (k_scores_dense: [Q,n_tiles+1,T], all terms)
+    u64* __restrict__ partial;             // [Q,splits,k] keys (0 = none)
+    u64* theta_q;                          // [Q] best known k-th key per query (shared by its CTAs)
+    u64* cand_global;                      // [Q*splits, cap] candidate buffers in global memory (large k), or NULL
+    float* __restrict__ dense_out;         // [Q,n_docs]  (k_scores_dense only)
+    u64 theta0;                            // initial threshold: key must be > theta0 to compete
     int Q, T, k;
-    int n_docs, tile_docs, n_tiles;       // tile_docs = S, documents per warp tile
-    int tiles_per_chunk, n_chunks;        // a chunk = the tiles one warp walks
-    int splits, tiles_per_split, cap;     // splits = CTAs per query (tiles_per_split: k_scores_dense)
-    int general;                          // 1: zero-score docs compete (weights may be <= 0)
-    int no_hot;                           // 1: always use the dense tile scan (A/B switch)
-    int wide_min;                         // average postings per tile from which a term takes the 128-wide path
+    int n_terms;
+    int n_docs, tile_docs, n_tiles;        // tile_docs = S, documents per warp tile
+    int tiles_per_chunk, n_chunks;         // a chunk = the tiles one warp walks
+    int splits, tiles_per_split, cap;      // splits = CTAs per query (tiles_per_split: k_scores_dense)
+    int general;                           // 1: zero-score docs compete (weights may be <= 0)
+    int no_hot;                            // 1: always use the dense tile scan (A/B switch)
+    int poison;                            // 1 (debug): fill the dynamic shared memory with 0xff before use
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -297,45 +373,65 @@ __global__ void __launch_bounds__(kThreads, 2) k_scores_dense(const SearchArgs a
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_score_topk (v4): the hot kernel.  Document-at-a-time streaming, one WARP per worker.
+// k_score_topk (v5): the hot kernel.  Document-at-a-time streaming, one WARP per worker, over the
+// re-bucketed index.
 //
 // CTA = (query, group of NCW document chunks); warp w of the CTA owns chunk sp*NCW + w, a
 // contiguous range of `tiles_per_chunk` document tiles of S = tile_docs documents, and a private
 // fp32 score tile of S slots in shared memory.  For every tile the warp walks the query's terms
-// strictly in query order; per term it keeps a cursor into the term's posting slice (the start
-// comes from the segment table, one entry per (query, chunk, term)) and pulls postings with
-// coalesced 128-byte loads -- 32 (narrow) or 128 (wide, for dense terms) at a time -- until the
-// first posting beyond the tile; each lane adds its in-tile postings into the score tile (one fp32
-// add per posting; a term has at most one posting per document and one warp handles every
-// posting of a document, so __syncwarp between terms is all the ordering needed: no atomics, no
-// CTA barriers, bit-identical to the reference's csc mat-vec).  A per-term "next doc id" lets the
-// warp skip terms with nothing in the tile without touching global memory.  After the last term
-// the warp pushes the documents that beat the running k-th best key into the CTA's candidate
-// buffer -- from the short list of slots whose running score reached the threshold during the
-// adds, followed by a write-only clear of the tile, or (list overflow / non-positive weights) by a
-// 16-byte vector scan + zero of all S slots.  The buffer is shared by the
-// NCW warps; when it overflows they meet in a (rare) named-barrier round, keep the k best and
-// raise the threshold, which is also published per query in global memory so that the other
-// CTAs of the query prune with it.
+// strictly in query order and adds each posting's weight into the tile: one fp32 add per posting,
+// a term has at most one posting per document and one warp handles every posting of a document,
+// so __syncwarp between terms is all the ordering needed -- no atomics, no CTA barriers,
+// bit-identical to the reference's csc mat-vec (bm25_native.py:152).
+//
+//  * heavy terms (a row in the tile table): the tile's posting range [lo, hi) comes from the table,
+//    whose entries for the next tiles are prefetched into the warp's state ring with 4-byte
+//    cp.async (LDGSTS) two tiles ahead.  The range is streamed in pieces of 128 postings, four
+//    consecutive postings per lane through two 16-byte loads (ids, weights); the piece after the
+//    current one -- of this term or of the next heavy term of the tile -- is requested before the
+//    current one is added.  No load address depends on a loaded doc id.  Postings of the
+//    neighbouring tiles (or padding) that the 16-byte granularity drags in fail the range test
+//    (unsigned)(doc - base) < S.
+//  * light terms: a cursor with the next two postings (doc id, weight) already resident in the
+//    state ring (refilled with cp.async when the cursor moves), so deciding that a light term has
+//    nothing in the tile costs one shared-memory read, and its postings are added by lane 0
+//    without waiting for global memory.
+//
+// After the last term the warp pushes the documents that beat the running k-th best key into the
+// CTA's candidate buffer -- from the short list of slots whose running score reached the threshold
+// during the adds, followed by a write-only clear of the tile, or (list overflow / non-positive
+// weights) by a 16-byte vector scan + zero of all S slots.  The buffer is shared by the NCW warps;
+// when it overflows they meet in a (rare) named-barrier round, keep the k best and raise the
+// threshold, which is also published per query in global memory so that the other CTAs of the
+// query prune with it.
 // shared memory (dynamic):
-//   float score[NCW][S] | u64 cand[cap] (unless in global memory) | int pos[NCW][T] | int cend[NCW][T] | int nxt[NCW][T]
+//   float score[NCW][S] | u64 cand[cap] (unless in global memory) | int state[NCW][kStateInts][T]
 //   | uint16 hot[NCW][kHotCap]
+// state (per warp, SoA over the T query terms):
+//   heavy term: rows 0..3 = ring of tile-table entries (entry of tile j in row j & 3), row 4 = table row
+//   light term: row 0 = cursor, 1 = end, 2/3 = next two doc ids, 4/5 = their weights
+//   row 7 = 1 for a heavy term, 0 for a light one
 // ---------------------------------------------------------------------------------------------
-constexpr int kDocNone = 0x7fffffff;
-constexpr int kSelectMin = 256;  // candidate sets larger than this are compacted by radix select
-
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 struct TopkState {
     u64* cand;
     int* s_ncand;
     int* s_overflow;
     int cap;
+    int general;    // zero / negative scores compete: the raw-score pre-filter must not clamp at 0
     u64 theta;      // key must be > theta to compete
-    float theta_f;  // cheap pre-filter on the raw score
+    float theta_f;  // cheap pre-filter on the raw score (never stricter than theta)
     __device__ __forceinline__ void set_theta(u64 t) {
         theta = t;
-        theta_f = (t == 0ull) ? -INFINITY : fmaxf(key_score(t), 1.401298464e-45f);
+        if (t == 0ull) theta_f = -INFINITY;
+        else theta_f = general ? key_score(t) : fmaxf(key_score(t), 1.401298464e-45f);
     }
     // returns false when the candidate buffer is full (the caller keeps the score in place)
     __device__ __forceinline__ bool push(float v, uint32_t doc) {
@@ -374,46 +470,87 @@ struct HotList {
     }
 };
 
-// 128 consecutive postings of one term, four per lane (lane, lane+32, lane+64, lane+96)
-struct PostingChunk {
-    int d0, d1, d2, d3;
-    float w0, w1, w2, w3;
-    __device__ __forceinline__ void load(const int32_t* __restrict__ ids, const float* __restrict__ w, int p, int r, int lane) {
-        const int l0 = lane, l1 = lane + 32, l2 = lane + 64, l3 = lane + 96;
-        d0 = l0 < r ? __ldg(ids + p + l0) : kDocNone;
-        d1 = l1 < r ? __ldg(ids + p + l1) : kDocNone;
-        d2 = l2 < r ? __ldg(ids + p + l2) : kDocNone;
-        d3 = l3 < r ? __ldg(ids + p + l3) : kDocNone;
-        w0 = l0 < r ? __ldg(w + p + l0) : 0.f;
-        w1 = l1 < r ? __ldg(w + p + l1) : 0.f;
-        w2 = l2 < r ? __ldg(w + p + l2) : 0.f;
-        w3 = l3 < r ? __ldg(w + p + l3) : 0.f;
-    }
-    __device__ __forceinline__ int doc(int i) const { return i == 0 ? d0 : (i == 1 ? d1 : (i == 2 ? d2 : d3)); }
-    // adds the postings with doc < tile_end into the tile; returns how many (a prefix: ids ascend)
-    __device__ __forceinline__ int add_into(float* scw, int base, int tile_end, HotList& hl, float theta_f) const {
-        const bool in0 = d0 < tile_end, in1 = d1 < tile_end, in2 = d2 < tile_end, in3 = d3 < tile_end;
-        // one term has at most one posting per document: the four slots are distinct
-        const float n0 = in0 ? scw[d0 - base] + w0 : 0.f;
-        const float n1 = in1 ? scw[d1 - base] + w1 : 0.f;
-        const float n2 = in2 ? scw[d2 - base] + w2 : 0.f;
-        const float n3 = in3 ? scw[d3 - base] + w3 : 0.f;
-        if (in0) scw[d0 - base] = n0;
-        if (in1) scw[d1 - base] = n1;
-        if (in2) scw[d2 - base] = n2;
-        if (in3) scw[d3 - base] = n3;
-        if (hl.active()) {
-            const bool h0 = in0 && n0 >= theta_f, h1 = in1 && n1 >= theta_f;
-            const bool h2 = in2 && n2 >= theta_f, h3 = in3 && n3 >= theta_f;
-            if (__any_sync(kFull, h0 | h1 | h2 | h3)) {
-                hl.add(h0, d0 - base);
-                hl.add(h1, d1 - base);
-                hl.add(h2, d2 - base);
-                hl.add(h3, d3 - base);
-            }
+// ---- explicit shared-memory accessors (32-bit shared-window addresses): the hot loop never
+// ---- re-derives a generic pointer
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ int lds_i32(unsigned a) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float lds_f32(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_i32(unsigned a, int v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_zero16(unsigned a) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
+}
+__device__ __forceinline__ void cp_async4_s(unsigned smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+// A piece of one heavy term's tile range: 128 consecutive postings starting at a multiple of 4,
+// four per lane (lane L holds postings p0 + 4L .. p0 + 4L + 3), fetched with two 16-byte loads.
+struct PostingPiece {
+    int4 d;
+    float4 w;
+    __device__ __forceinline__ void load(const int32_t* __restrict__ ids, const float* __restrict__ wts, int p0, int hi,
+                                         int lane) {
+        const int idx = p0 + 4 * lane;
+        d = make_int4(kDocNone, kDocNone, kDocNone, kDocNone);
+        w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < hi) {
+            d = __ldg(reinterpret_cast<const int4*>(ids + idx));
+            w = __ldg(reinterpret_cast<const float4*>(wts + idx));
         }
-        return __popc(__ballot_sync(kFull, in0)) + __popc(__ballot_sync(kFull, in1)) +
-               __popc(__ballot_sync(kFull, in2)) + __popc(__ballot_sync(kFull, in3));
+    }
+    // Adds the postings whose doc id lies in [base, base + S) into the tile at shared address
+    // `tile`.  One term has at most one posting per document, so the four slots are distinct and
+    // the four read-modify-writes are independent: predicated (never branching), loads first.
+    // n0..n3 = the new scores (0 for postings outside the tile).
+    __device__ __forceinline__ void add_into(unsigned tile, int base, unsigned S, float& n0, float& n1, float& n2,
+                                             float& n3) const {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p0, p1, p2, p3;\n\t"
+            ".reg .u32 s0, s1, s2, s3;\n\t"
+            ".reg .f32 v0, v1, v2, v3;\n\t"
+            "sub.u32 s0, %4, %12;\n\t"
+            "sub.u32 s1, %5, %12;\n\t"
+            "sub.u32 s2, %6, %12;\n\t"
+            "sub.u32 s3, %7, %12;\n\t"
+            "setp.lt.u32 p0, s0, %13;\n\t"
+            "setp.lt.u32 p1, s1, %13;\n\t"
+            "setp.lt.u32 p2, s2, %13;\n\t"
+            "setp.lt.u32 p3, s3, %13;\n\t"
+            "mad.lo.u32 s0, s0, 4, %14;\n\t"
+            "mad.lo.u32 s1, s1, 4, %14;\n\t"
+            "mad.lo.u32 s2, s2, 4, %14;\n\t"
+            "mad.lo.u32 s3, s3, 4, %14;\n\t"
+            "mov.f32 %0, 0f00000000;\n\t"
+            "mov.f32 %1, 0f00000000;\n\t"
+            "mov.f32 %2, 0f00000000;\n\t"
+            "mov.f32 %3, 0f00000000;\n\t"
+            "@p0 ld.shared.f32 v0, [s0];\n\t"
+            "@p1 ld.shared.f32 v1, [s1];\n\t"
+            "@p2 ld.shared.f32 v2, [s2];\n\t"
+            "@p3 ld.shared.f32 v3, [s3];\n\t"
+            "@p0 add.f32 %0, v0, %8;\n\t"
+            "@p1 add.f32 %1, v1, %9;\n\t"
+            "@p2 add.f32 %2, v2, %10;\n\t"
+            "@p3 add.f32 %3, v3, %11;\n\t"
+            "@p0 st.shared.f32 [s0], %0;\n\t"
+            "@p1 st.shared.f32 [s1], %1;\n\t"
+            "@p2 st.shared.f32 [s2], %2;\n\t"
+            "@p3 st.shared.f32 [s3], %3;\n\t"
+            "}"
+            : "=&f"(n0), "=&f"(n1), "=&f"(n2), "=&f"(n3)
+            : "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w), "r"(base), "r"(S),
+              "r"(tile)
+            : "memory");
     }
 };
 
@@ -451,10 +588,8 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     // pushes are rare once the threshold has settled, and the freed shared memory buys a third CTA per SM
     u64* cand_smem = reinterpret_cast<u64*>(sc + (size_t)NCW * S);
     u64* cand = a.cand_global ? a.cand_global + (size_t)blockIdx.x * cap : cand_smem;
-    int* st_pos = reinterpret_cast<int*>(cand_smem + (a.cand_global ? 0 : cap));
-    int* st_end = st_pos + NCW * T;
-    int* st_nxt = st_end + NCW * T;
-    unsigned short* st_hot = reinterpret_cast<unsigned short*>(st_nxt + NCW * T);
+    int* st_all = reinterpret_cast<int*>(cand_smem + (a.cand_global ? 0 : cap));
+    unsigned short* st_hot = reinterpret_cast<unsigned short*>(st_all + (size_t)NCW * kStateInts * T);
     __shared__ int s_ncand, s_overflow;
     __shared__ u64 s_theta;
     __shared__ int s_hist[264];  // select_candidates scratch
@@ -467,6 +602,13 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     const int chunk = sp * NCW + warp;
     const WarpsGroup grp{(int)blockDim.x, tid};
 
+    if (a.poison) {  // debug: no read of uninitialised shared memory may go unnoticed
+        unsigned* all = reinterpret_cast<unsigned*>(smem_raw);
+        const size_t words = ((size_t)NCW * S * 4 + (a.cand_global ? 0 : (size_t)cap * 8) +
+                              (size_t)NCW * kStateInts * T * 4 + (size_t)NCW * kHotCap * 2) / 4;
+        for (size_t i = tid; i < words; i += blockDim.x) all[i] = 0xffffffffu;
+        __syncthreads();
+    }
     float* scw = sc + (size_t)warp * S;
     for (int i = lane * 4; i < S; i += 128) *reinterpret_cast<float4*>(scw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
@@ -477,7 +619,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     }
     __syncthreads();
 
-    TopkState tk{cand, &s_ncand, &s_overflow, cap, 0ull, 0.f};
+    TopkState tk{cand, &s_ncand, &s_overflow, cap, a.general, 0ull, 0.f};
     tk.set_theta(s_theta);
     bool leftover = false;       // this warp's tile still holds scores that did not fit in cand
     uint32_t left_doc0 = 0;
@@ -512,115 +654,167 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     };
 
     if (chunk < a.n_chunks) {
-        int* pos_w = st_pos + warp * T;
-        int* end_w = st_end + warp * T;
-        int* nxt_w = st_nxt + warp * T;
+        const unsigned T4 = (unsigned)T * 4u;                                            // bytes per state row
+        const unsigned st = smem_u32(st_all + (size_t)warp * kStateInts * T);             // this warp's state
+        const unsigned tile = smem_u32(scw);                                             // this warp's score tile
+        const unsigned uS = (unsigned)S;
+        const int NB = a.n_tiles;
+        const int j0 = chunk * a.tiles_per_chunk;
+        const int j1 = min(NB, j0 + a.tiles_per_chunk);
         const int32_t* seg0 = a.seg + ((int64_t)q * (a.n_chunks + 1) + chunk) * T;
         for (int t = lane; t < T; t += 32) {
-            const int p = __ldg(seg0 + t), e = __ldg(seg0 + T + t);
-            pos_w[t] = p;
-            end_w[t] = e;
-            nxt_w[t] = (p < e) ? __ldg(a.ids + p) : kDocNone;
+            const int term = __ldg(a.queries + (int64_t)q * T + t);
+            const bool valid = term >= 0 && term < a.n_terms;
+            const int row = valid ? __ldg(a.term_row + term) : -1;
+            const unsigned s = st + 4u * t;
+            if (row >= 0) {
+                const int32_t* tr = a.tab + (int64_t)row * (NB + 1);
+                sts_i32(s + ((j0 + 0) & 3) * T4, __ldg(tr + j0));
+                sts_i32(s + ((j0 + 1) & 3) * T4, __ldg(tr + min(j0 + 1, NB)));
+                sts_i32(s + ((j0 + 2) & 3) * T4, __ldg(tr + min(j0 + 2, NB)));
+                sts_i32(s + ((j0 + 3) & 3) * T4, 0);
+                sts_i32(s + 4 * T4, row);
+                sts_i32(s + 7 * T4, 1);
+            } else {
+                int p = 0, e = 0;
+                if (valid) {
+                    p = __ldg(seg0 + t);
+                    e = __ldg(seg0 + T + t);
+                }
+                sts_i32(s + 0 * T4, p);
+                sts_i32(s + 1 * T4, e);
+                sts_i32(s + 2 * T4, p < e ? __ldg(a.ids + p) : kDocNone);
+                sts_i32(s + 4 * T4, p < e ? __float_as_int(__ldg(a.w + p)) : 0);
+                sts_i32(s + 3 * T4, p + 1 < e ? __ldg(a.ids + p + 1) : kDocNone);
+                sts_i32(s + 5 * T4, p + 1 < e ? __float_as_int(__ldg(a.w + p + 1)) : 0);
+                sts_i32(s + 7 * T4, 0);
+            }
         }
-        __syncwarp();
-        const int j0 = chunk * a.tiles_per_chunk;
-        const int j1 = min(a.n_tiles, j0 + a.tiles_per_chunk);
         for (int j = j0; j < j1; ++j) {
+            cp_async_wait_all();  // table entries / cursor refills requested during the previous tiles
+            __syncwarp();
             const int base = j * S;
             const int tile_end = base + S;
             bool touched = false;
+            bool refill_inflight = false;  // a light-term refill was requested during THIS tile
             hl.reset(!a.general && !a.no_hot);
-            // ---- accumulate: terms strictly in query order ------------------------------------
-            // Dense terms (>= wide_min postings per remaining tile on average) stream 128 postings
-            // per step with the next step's loads already in flight.  Runs of sparse terms are taken
-            // up to four at a time: the first 32 postings of each are requested together
-            // (memory-level parallelism across terms), then added one term after the other.
-            const int wide_cut = a.wide_min * (j1 - j);
-            for (int g0 = 0; g0 < T; g0 += 32) {
-                const int tl = g0 + lane;
-                unsigned act = __ballot_sync(kFull, tl < T && nxt_w[min(tl, T - 1)] < tile_end);
-                if (act) touched = true;
-                while (act) {
-                    const int t0 = g0 + __ffs(act) - 1;
-                    int p = pos_w[t0];
-                    int e = end_w[t0];
-                    if (e - p >= wide_cut) {
-                        act &= act - 1;
-                        int nx = kDocNone;
-                        PostingChunk A, B;
-                        A.load(a.ids, a.w, p, e - p, lane);
-                        for (;;) {
-                            B.load(a.ids, a.w, p + 128, e - p - 128, lane);
-                            const int c = A.add_into(scw, base, tile_end, hl, tk.theta_f);
-                            p += c;
-                            if (c < 128) {  // the first posting beyond the tile (if any) is element c
-                                nx = __shfl_sync(kFull, A.doc(c >> 5), c & 31);
-                                break;
-                            }
-                            if (p >= e) break;
-                            A = B;
-                        }
+            const unsigned r0 = st + (j & 3) * T4, r1 = st + ((j + 1) & 3) * T4, r3 = st + ((j + 3) & 3) * T4;
+            const int jn = min(j + 3, NB);
+
+            // light terms of `mask` (bit b = term g0 + b), in query order; lane 0 adds, from the
+            // cursor's resident postings
+            auto light_visits = [&](unsigned mask, int g0) {
+                while (mask) {
+                    const unsigned s = st + 4u * (g0 + __ffs(mask) - 1);
+                    mask &= mask - 1;
+                    for (;;) {
+                        const int hd = lds_i32(s + 2 * T4);
+                        if (hd >= tile_end) break;
+                        bool hot = false;
                         if (lane == 0) {
-                            pos_w[t0] = p;
-                            nxt_w[t0] = nx;
+                            const unsigned slot = tile + 4u * (unsigned)(hd - base);
+                            const float nw = lds_f32(slot) + __int_as_float(lds_i32(s + 4 * T4));
+                            sts_f32(slot, nw);
+                            hot = nw >= tk.theta_f;
+                        }
+                        if (hl.active()) hl.add(hot, hd - base);
+                        if (refill_inflight) {  // the second resident posting may still be on its way
+                            cp_async_wait_all();
+                            refill_inflight = false;
                         }
                         __syncwarp();
-                        continue;
-                    }
-                    int tt[4] = {-1, -1, -1, -1}, pp[4], ee[4], dd[4];
-                    float ww[4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (act) {
-                            const int t = g0 + __ffs(act) - 1;
-                            const int pt = pos_w[t], et = end_w[t];
-                            const int r = et - pt;
-                            if (g == 0 || r < wide_cut) {  // a dense term ends the run (handled above next)
-                                act &= act - 1;
-                                tt[g] = t;
-                                pp[g] = pt;
-                                ee[g] = et;
-                                dd[g] = lane < r ? __ldg(a.ids + pt + lane) : kDocNone;
-                                ww[g] = lane < r ? __ldg(a.w + pt + lane) : 0.f;
-                            } else {
-                                break;
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (tt[g] < 0) break;  // warp-uniform
-                        p = pp[g];
-                        e = ee[g];
-                        int nx = kDocNone;
-                        int d = dd[g];
-                        float w = ww[g];
-                        for (;;) {
-                            const bool in = d < tile_end;
-                            float nw = 0.f;
-                            if (in) {
-                                nw = scw[d - base] + w;
-                                scw[d - base] = nw;
-                            }
-                            if (hl.active()) hl.add(in && nw >= tk.theta_f, d - base);
-                            const int c = __popc(__ballot_sync(kFull, in));
-                            p += c;
-                            if (c < 32) {
-                                nx = __shfl_sync(kFull, d, c);
-                                break;
-                            }
-                            if (p >= e) break;
-                            const int r = e - p;
-                            d = lane < r ? __ldg(a.ids + p + lane) : kDocNone;
-                            w = lane < r ? __ldg(a.w + p + lane) : 0.f;
-                        }
                         if (lane == 0) {
-                            pos_w[tt[g]] = p;
-                            nxt_w[tt[g]] = nx;
+                            const int pos = lds_i32(s) + 1, e = lds_i32(s + T4);
+                            sts_i32(s, pos);
+                            sts_i32(s + 2 * T4, lds_i32(s + 3 * T4));
+                            sts_i32(s + 4 * T4, lds_i32(s + 5 * T4));
+                            if (pos + 1 < e) {
+                                cp_async4_s(s + 3 * T4, a.ids + pos + 1);
+                                cp_async4_s(s + 5 * T4, a.w + pos + 1);
+                            } else {
+                                sts_i32(s + 3 * T4, kDocNone);
+                            }
                         }
+                        refill_inflight = true;
                         __syncwarp();
                     }
                 }
+            };
+
+            // ---- accumulate: terms strictly in query order ------------------------------------
+            for (int g0 = 0; g0 < T; g0 += 32) {
+                const int t = g0 + lane;
+                int lo = 0, hi = 0, hd = kDocNone;
+                if (t < T) {
+                    const unsigned s = 4u * t;
+                    if (lds_i32(st + 7 * T4 + s)) {
+                        lo = lds_i32(r0 + s);
+                        hi = lds_i32(r1 + s);
+                        cp_async4_s(r3 + s, a.tab + (int64_t)lds_i32(st + 4 * T4 + s) * (NB + 1) + jn);
+                    } else {
+                        hd = lds_i32(st + 2 * T4 + s);
+                    }
+                }
+                unsigned hm = __ballot_sync(kFull, hi > lo);        // heavy terms with postings in this tile
+                unsigned lm = __ballot_sync(kFull, hd < tile_end);  // light terms with postings in this tile
+                if ((hm | lm) == 0u) continue;
+                touched = true;
+                // piece generator over the heavy terms of the group (warp-uniform state)
+                int gp = 0, ghi = 0, gt = 0;
+                auto next_piece = [&](bool& first) -> bool {
+                    if (gp + 128 < ghi) {
+                        gp += 128;
+                        first = false;
+                        return true;
+                    }
+                    if (hm == 0u) return false;
+                    gt = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    gp = __shfl_sync(kFull, lo, gt) & ~3;
+                    ghi = __shfl_sync(kFull, hi, gt);
+                    first = true;
+                    return true;
+                };
+                auto consume = [&](const PostingPiece& P, bool first, int tt) {
+                    if (first) {  // a new term: first the light terms that precede it in the query
+                        const unsigned pl = lm & ((1u << tt) - 1u);
+                        if (pl) {
+                            __syncwarp();
+                            lm &= ~pl;
+                            light_visits(pl, g0);
+                        }
+                        __syncwarp();
+                    }
+                    float n0, n1, n2, n3;
+                    P.add_into(tile, base, uS, n0, n1, n2, n3);
+                    if (hl.active()) {  // postings outside the tile give n = 0 < theta_f
+                        if (__any_sync(kFull, fmaxf(fmaxf(n0, n1), fmaxf(n2, n3)) >= tk.theta_f)) {
+                            hl.add(n0 >= tk.theta_f, P.d.x - base);
+                            hl.add(n1 >= tk.theta_f, P.d.y - base);
+                            hl.add(n2 >= tk.theta_f, P.d.z - base);
+                            hl.add(n3 >= tk.theta_f, P.d.w - base);
+                        }
+                    }
+                };
+                // ping-pong: the piece after the current one is requested before the current one is added
+                PostingPiece A, B;
+                bool fA = false, fB = false;
+                bool more = next_piece(fA);
+                int tA = gt, tB = 0;
+                if (more) A.load(a.ids, a.w, gp, ghi, lane);
+                while (more) {
+                    more = next_piece(fB);
+                    tB = gt;
+                    if (more) B.load(a.ids, a.w, gp, ghi, lane);
+                    consume(A, fA, tA);
+                    if (!more) break;
+                    more = next_piece(fA);
+                    tA = gt;
+                    if (more) A.load(a.ids, a.w, gp, ghi, lane);
+                    consume(B, fB, tB);
+                }
+                __syncwarp();
+                if (lm) light_visits(lm, g0);
             }
             // ---- epilogue: push the documents that beat the k-th best so far, clear the tile ---
             if (touched || a.general) {
@@ -635,9 +829,9 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
                         const int x = i < hl.n ? (int)hl.slots[i] : -1 - lane;
                         const unsigned same = __match_any_sync(kFull, x);  // a slot may be listed twice
                         if (x >= 0 && (__ffs(same) - 1) == lane) {
-                            const float v = scw[x];
+                            const float v = lds_f32(tile + 4u * x);
                             if (v > 0.f) {  // not yet taken by an earlier step of this loop
-                                if (tk.push(v, (uint32_t)(base + x))) scw[x] = 0.f;
+                                if (tk.push(v, (uint32_t)(base + x))) sts_f32(tile + 4u * x, 0.f);
                                 else left = true;
                             }
                         }
@@ -645,8 +839,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
                     }
                     left = __any_sync(kFull, left);
                     if (!left) {
-                        for (int idx = lane * 4; idx < S; idx += 128)
-                            *reinterpret_cast<float4*>(scw + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (unsigned off = lane * 16u; off < uS * 4u; off += 512u) sts_zero16(tile + off);
                     }
                 }
                 if (__any_sync(kFull, left)) {  // candidate buffer full: the overflow round rescans this tile
@@ -660,6 +853,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
                 overflow_round();
             }
         }
+        cp_async_wait_all();  // nothing of this warp may still be in flight towards shared memory
     }
     for (;;) {  // finished: keep serving overflow rounds until every warp of the CTA is here
         grp.sync();
@@ -727,7 +921,8 @@ __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
                 } else {
                     const int l = e / a.k_in, r = e - l * a.k_in;
                     const int64_t off = (int64_t)l * a.list_stride + q * a.k_in + r;
-                    key = make_key(a.in_scores[off], (uint32_t)a.in_ids[off]);
+                    const int32_t id = a.in_ids[off];  // negative: padding of a shard with fewer than k_in documents
+                    key = id < 0 ? 0ull : make_key(a.in_scores[off], (uint32_t)id);
                 }
             }
             buf[have + i] = key;
@@ -774,13 +969,13 @@ __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
 // min(df_t, kBoundSample) postings of term t, or 0 when the term has fewer postings.  One CTA of
 // 128 threads per term; the sample is sorted in shared memory (as order-preserving keys).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_term_bounds(const int32_t* __restrict__ indptr, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) k_term_bounds(const int2* __restrict__ tptr, const float* __restrict__ w,
                                                      int n_terms, float* __restrict__ bounds) {
     __shared__ u64 buf[kBoundSample];
     const int t = blockIdx.x;
     const int tid = threadIdx.x;
-    const int lo = indptr[t];
-    const int m = min(indptr[t + 1] - lo, kBoundSample);
+    const int lo = tptr[t].x;
+    const int m = min(tptr[t].y - lo, kBoundSample);
     float* out = bounds + (int64_t)t * kBoundLevels;
     if (m < 1) {
         if (tid < kBoundLevels) out[tid] = 0.f;

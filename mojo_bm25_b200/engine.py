@@ -47,7 +47,8 @@ class DeviceIndex:
     @classmethod
     def from_torch(cls, indptr, indices, data, n_docs: int, doc_id_base: int = 0, borrow: bool = True):
         """Build from CUDA tensors already in HBM (int32 indptr/indices, fp32 data, canonical CSC).
-        With ``borrow`` the tensors are used in place (kept alive by this object)."""
+        The library re-buckets the index into its own memory during this call; ``borrow`` is kept
+        for source compatibility and no longer keeps the tensors alive."""
         import torch
 
         lib = _lib.load()
@@ -60,7 +61,7 @@ class DeviceIndex:
         self = cls.__new__(cls)
         self._h = ctypes.c_void_p()
         self.device = indices.device.index or 0
-        self._keepalive = (indptr, indices, data) if borrow else None
+        self._keepalive = None
         _lib.check(lib.bm25_index_create_device(
             ctypes.c_void_p(indptr.data_ptr()), ctypes.c_void_p(indices.data_ptr()),
             ctypes.c_void_p(data.data_ptr()), indptr.numel() - 1, int(n_docs), indices.numel(),

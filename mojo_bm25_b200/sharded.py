@@ -31,14 +31,21 @@ def doc_range_of_rank(n_docs: int, world: int, rank: int) -> Tuple[int, int]:
 
 class DocShardedSearcher:
     def __init__(self, local_search, k: int, merge: Optional[Callable] = None,
-                 group: Optional[dist.ProcessGroup] = None):
+                 group: Optional[dist.ProcessGroup] = None, shard_docs=None):
         """``local_search(queries, k, out_ids, out_scores)`` fills the two [Q,k] outputs with the
         shard-local top-k (GLOBAL doc ids); pass a LIST of such callables when this rank owns
         several document shards (a corpus of more than 2^31 postings on few GPUs: every shard is
         its own int32-indexed handle).  Every rank must own the same number of shards.
         ``merge(ids_view, scores_view, k, list_stride, n_lists, n_queries, k_in)`` defaults to the
-        CUDA merge kernel."""
+        CUDA merge kernel.  ``shard_docs[s]`` = number of documents of local shard ``s``: a shard
+        with fewer than k documents (the tail shard of a small corpus, or an empty one) is searched
+        with k_local = its size and its list is padded with (id -1, score -inf) entries, which the
+        merge ignores -- the global k <= N stays valid although the reference's k <= n_docs rule
+        (bm25_native.py:204-214) would reject the shard-local call."""
         self.local_searches = list(local_search) if isinstance(local_search, (list, tuple)) else [local_search]
+        self.shard_docs = None if shard_docs is None else [int(n) for n in shard_docs]
+        if self.shard_docs is not None and len(self.shard_docs) != len(self.local_searches):
+            raise ValueError("shard_docs must name one size per local shard")
         self.k = int(k)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -58,7 +65,7 @@ class DocShardedSearcher:
         def make(ix):
             return lambda q, kk, oi, os_: ix.search_device(q, kk, out_ids=oi, out_scores=os_)
 
-        return cls([make(ix) for ix in idxs], k, group=group)
+        return cls([make(ix) for ix in idxs], k, group=group, shard_docs=[ix.n_docs for ix in idxs])
 
     def _buffers(self, n_queries: int, device):
         n_local = len(self.local_searches)
@@ -74,7 +81,18 @@ class DocShardedSearcher:
         n_local = len(self.local_searches)
         send, recv = self._buffers(n_queries, queries.device)
         for s, local in enumerate(self.local_searches):
-            local(queries, self.k, send[s, 0], send[s, 1].view(torch.float32))
+            k_local = self.k if self.shard_docs is None else min(self.k, self.shard_docs[s])
+            if k_local == self.k:
+                local(queries, self.k, send[s, 0], send[s, 1].view(torch.float32))
+                continue
+            send[s, 0].fill_(-1)
+            send[s, 1].view(torch.float32).fill_(float("-inf"))
+            if k_local > 0:
+                ids = torch.empty((n_queries, k_local), dtype=torch.int32, device=queries.device)
+                sc = torch.empty((n_queries, k_local), dtype=torch.float32, device=queries.device)
+                local(queries, k_local, ids, sc)
+                send[s, 0, :, :k_local].copy_(ids)
+                send[s, 1, :, :k_local].view(torch.float32).copy_(sc)
         if self.world > 1:
             dist.all_gather_into_tensor(recv.view(self.world * n_local * 2, n_queries, self.k),
                                         send.view(n_local * 2, n_queries, self.k), group=self.group)

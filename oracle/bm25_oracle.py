@@ -258,10 +258,12 @@ def partition_csc_by_doc_range(indptr, indices, data, n_docs: int, n_shards: int
 
 def merge_topk_lists(ids: np.ndarray, scores: np.ndarray, k: int):
     """Merge ``L`` per-shard candidate lists ``ids/scores [L, Q, k_in]`` into a global top-k
-    ordered by (score descending, doc id ascending)."""
+    ordered by (score descending, doc id ascending).  Entries with a negative id are padding of
+    shards that hold fewer than k_in documents and never win."""
     l_n, q_n, k_in = ids.shape
     flat_ids = np.transpose(ids, (1, 0, 2)).reshape(q_n, l_n * k_in)
-    flat_sc = np.transpose(scores, (1, 0, 2)).reshape(q_n, l_n * k_in)
+    flat_sc = np.transpose(scores, (1, 0, 2)).reshape(q_n, l_n * k_in).copy()
+    flat_sc[flat_ids < 0] = -np.inf
     out_i = np.zeros((q_n, k), np.int32)
     out_s = np.zeros((q_n, k), np.float32)
     for q in range(q_n):

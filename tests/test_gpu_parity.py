@@ -267,8 +267,11 @@ def test_every_launch_shape_gives_identical_results(engine, workload, scale, k):
         dict(no_priming=1, cap=k + 64, splits=1), dict(no_theta_share=1, splits=5), dict(consumer_warps=16, tile_docs=1024),
         dict(consumer_warps=12, tile_docs=4096, splits=2), dict(consumer_warps=1, tile_docs=128, splits=3),
         dict(waves=1), dict(waves=20, no_hot=1, no_priming=1),
+        dict(heavy_min=1), dict(heavy_min=1 << 20), dict(heavy_min=256, tile_docs=1024, poison=1),
+        dict(heavy_min=1 << 20, cap=k + 64, consumer_warps=3, poison=1),
     ]
-    names = ["cap", "consumer_warps", "tile_docs", "no_hot", "no_priming", "no_theta_share", "splits", "waves"]
+    names = ["cap", "consumer_warps", "tile_docs", "no_hot", "no_priming", "no_theta_share", "splits", "waves",
+             "heavy_min", "poison"]
     for v in variants:
         for n in names:
             index.set_option(n, v.get(n, 0))
@@ -325,7 +328,8 @@ def test_fuzz_random_indices_and_knobs(engine):
         k = int(min(n_docs, rng.choice([1, 3, 10, 100, 1000])))
         for name, choices in [("tile_docs", [0, 128, 512, 4096]), ("consumer_warps", [0, 1, 3, 8, 16]),
                               ("splits", [0, 1, 2, 9]), ("cap", [0, k + 64]), ("no_hot", [0, 1]),
-                              ("no_priming", [0, 1]), ("no_theta_share", [0, 1]), ("wide_min", [0, 1, 10000])]:
+                              ("no_priming", [0, 1]), ("no_theta_share", [0, 1]), ("heavy_min", [0, 1, 512, 1 << 20]),
+                              ("poison", [0, 1])]:
             index.set_option(name, int(rng.choice(choices)))
         _check_batch(index, indptr, indices, data, n_docs, q, k)
         index.close()
