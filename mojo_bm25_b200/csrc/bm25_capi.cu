@@ -166,7 +166,7 @@ struct bm25_index {
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
     int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_heavy_min = 0, opt_cand_smem = 0;
-    int opt_poison = 0;
+    int opt_poison = 0, opt_no_bulk_clear = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace: one per handle; searches on different streams are ordered through ws_done
@@ -471,9 +471,9 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
         k_scores_dense<<<(unsigned)grid, kThreads, lp.smem, st>>>(a);
     } else {
         static thread_local size_t configured[2][64] = {{0}, {0}};
-        if (lp.warps <= 8) {
-            if ((rc = configure_smem(k_score_topk<256>, lp.smem, ix->smem_optin, &configured[0][ix->device % 64]))) return rc;
-            k_score_topk<256><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
+        if (lp.warps <= BM25_LB_T / 32) {
+            if ((rc = configure_smem(k_score_topk<BM25_LB_T>, lp.smem, ix->smem_optin, &configured[0][ix->device % 64]))) return rc;
+            k_score_topk<BM25_LB_T><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
         } else {
             if ((rc = configure_smem(k_score_topk<512>, lp.smem, ix->smem_optin, &configured[1][ix->device % 64]))) return rc;
             k_score_topk<512><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
@@ -578,6 +578,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.general = lp.general;
     a.no_hot = ix->opt_no_hot;
     a.poison = ix->opt_poison;
+    a.bulk_clear = ix->opt_no_bulk_clear ? 0 : 1;
     if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
     MergeArgs m{};
@@ -826,6 +827,8 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
     } else if (!strcmp(name, "heavy_min")) {
         if (value < 0 || value > (1 << 28)) return fail(BM25_ERR_INVALID, "heavy_min out of range");
         ix->opt_heavy_min = (int)value;
+    } else if (!strcmp(name, "no_bulk_clear")) {
+        ix->opt_no_bulk_clear = value ? 1 : 0;
     } else if (!strcmp(name, "poison")) {
         ix->opt_poison = value ? 1 : 0;
     } else if (!strcmp(name, "cand_smem")) {

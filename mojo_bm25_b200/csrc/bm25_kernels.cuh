@@ -332,6 +332,7 @@ struct SearchArgs {
     int general;                           // 1: zero-score docs compete (weights may be <= 0)
     int no_hot;                            // 1: always use the dense tile scan (A/B switch)
     int poison;                            // 1 (debug): fill the dynamic shared memory with 0xff before use
+    int bulk_clear;                        // 1: clear the score tile with st.bulk (UMEMSETS) instead of vector stores
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -488,6 +489,11 @@ __device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.
 __device__ __forceinline__ void sts_zero16(unsigned a) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0) : "memory");
 }
+// Blackwell bulk zero-fill of shared memory (PTX st.bulk, SASS UMEMSETS): one warp-uniform
+// instruction instead of bytes/512 vector stores through the LSU pipe.  bytes: multiple of 8.
+__device__ __forceinline__ void smem_bulk_zero(unsigned a, unsigned bytes) {
+    asm volatile("st.bulk.weak.shared::cta [%0], %1, 0;" ::"r"(a), "l"((unsigned long long)bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async4_s(unsigned smem_dst, const void* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
@@ -577,22 +583,144 @@ __device__ __forceinline__ bool tile_scan(float* scw, int S, int nd_w, uint32_t 
     return left;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Rare paths of k_score_topk, kept out of line (__noinline__) so that their state -- candidate
+// buffer, thresholds, output pointers -- does not occupy registers in the hot tile loop.
+// ---------------------------------------------------------------------------------------------
+struct CtaShared {
+    int ncand, overflow;
+    u64 theta;
+    int hist[264];  // select_candidates scratch
+};
+
+struct ColdCtx {
+    u64* cand;       // candidate buffer of this CTA (shared or global memory)
+    u64* out;        // this CTA's k output keys (also select scratch)
+    u64* theta_q;    // per-query shared threshold slot, or NULL
+    u64 theta0;
+    CtaShared* sh;
+    float* scw;      // this warp's score tile
+    unsigned short* hot;
+    int cap, k, S, general, nthreads, tid;
+};
+
+// candidate-buffer overflow round: every warp of the CTA takes part.  `leftover`: this warp's tile
+// (documents left_doc0 .. left_doc0 + left_nd) still holds scores that did not fit in the buffer.
+__device__ __forceinline__ void overflow_round(const ColdCtx& c, TopkState& tk, bool leftover, uint32_t left_doc0,
+                                               int left_nd) {
+    const WarpsGroup grp{c.nthreads, c.tid};
+    const int lane = c.tid & 31;
+    for (;;) {
+        if (c.cap > kSelectMin)  // a round is only entered with a full buffer (n = cap > k)
+            select_candidates(c.cand, c.cap, c.k, c.out, c.sh->hist, &c.sh->ncand, &c.sh->theta, true, grp);
+        else
+            compact_candidates(c.cand, c.cap, c.k, c.theta0, &c.sh->ncand, &c.sh->theta, grp);
+        if (c.tid == 0) {
+            c.sh->overflow = 0;
+            if (c.theta_q) {  // share the threshold with the other CTAs of this query
+                const u64 mine = c.sh->theta;
+                const u64 old = atomicMax(c.theta_q, mine);
+                if (old > mine) c.sh->theta = old;
+            }
+        }
+        grp.sync();
+        tk.set_theta(c.sh->theta);
+        if (leftover) leftover = __any_sync(kFull, tile_scan(c.scw, c.S, left_nd, left_doc0, lane, tk));
+        grp.sync();
+        const int again = ld_volatile(&c.sh->overflow);
+        grp.sync();
+        if (!again) break;
+    }
+}
+
+// End of a tile that needs more than the write-only clear: pushes the documents that beat the k-th
+// best so far into the candidate buffer -- from the hot list (hl_n <= kHotCap entries) or by a
+// full scan -- clears the tile, and serves a candidate-buffer overflow round if one is pending.
+// Returns the (possibly raised) raw-score pre-filter threshold.
+__device__ __noinline__ float tile_finish(const ColdCtx c, int base, int nd_w, int hl_n, int use_list) {
+    const int lane = c.tid & 31;
+    TopkState tk{c.cand, &c.sh->ncand, &c.sh->overflow, c.cap, c.general, 0ull, 0.f};
+    tk.set_theta(c.sh->theta);  // thresholds only change inside rounds, which every warp attends
+    bool left = false;
+    if (!use_list) {
+        left = tile_scan(c.scw, c.S, nd_w, (uint32_t)base, lane, tk);  // reads, tests and zeroes all S slots
+    } else {
+        __syncwarp();
+        for (int i0 = 0; i0 < hl_n; i0 += 32) {
+            const int i = i0 + lane;
+            const int x = i < hl_n ? (int)c.hot[i] : -1 - lane;
+            const unsigned same = __match_any_sync(kFull, x);  // a slot may be listed twice
+            if (x >= 0 && (__ffs(same) - 1) == lane) {
+                const float v = c.scw[x];
+                if (v > 0.f) {  // not yet taken by an earlier step of this loop
+                    if (tk.push(v, (uint32_t)(base + x))) c.scw[x] = 0.f;
+                    else left = true;
+                }
+            }
+            __syncwarp();
+        }
+        left = __any_sync(kFull, left);
+        if (!left)
+            for (int idx = lane * 4; idx < c.S; idx += 128)
+                *reinterpret_cast<float4*>(c.scw + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    left = __any_sync(kFull, left);
+    if (left || ld_volatile(&c.sh->overflow)) {
+        const WarpsGroup grp{c.nthreads, c.tid};
+        grp.sync();
+        overflow_round(c, tk, left, (uint32_t)base, nd_w);
+    }
+    return tk.theta_f;
+}
+
+// After a warp's last tile: keep serving overflow rounds until every warp of the CTA is here, then
+// write the CTA's k best keys.
+__device__ __noinline__ void cta_finish(const ColdCtx c, int q_has_theta) {
+    const WarpsGroup grp{c.nthreads, c.tid};
+    TopkState tk{c.cand, &c.sh->ncand, &c.sh->overflow, c.cap, c.general, 0ull, 0.f};
+    tk.set_theta(c.sh->theta);
+    for (;;) {
+        grp.sync();
+        if (!ld_volatile(&c.sh->overflow)) break;
+        overflow_round(c, tk, false, 0u, 0);
+    }
+    const int n_end = min(ld_volatile(&c.sh->ncand), c.cap);
+    if (n_end > kSelectMin && n_end > c.k) {
+        // the k keepers go straight to the output slot, unsorted (k_merge sorts what it loads)
+        select_candidates(c.cand, n_end, c.k, c.out, c.sh->hist, &c.sh->ncand, &c.sh->theta, false, grp);
+        if (c.tid == 0 && c.theta_q) atomicMax(c.theta_q, c.sh->theta);
+        return;
+    }
+    if (q_has_theta /* candidate buffer in global memory */) {
+        // here n_end <= k (a larger set went through the select above): everything is a keeper, unsorted
+        for (int i = c.tid; i < c.k; i += c.nthreads) c.out[i] = (i < n_end) ? c.cand[i] : 0ull;
+        return;
+    }
+    compact_candidates(c.cand, c.cap, c.k, c.theta0, &c.sh->ncand, &c.sh->theta, grp);
+    if (c.tid == 0 && c.theta_q && c.sh->ncand >= c.k) atomicMax(c.theta_q, c.sh->theta);
+    const int n = c.sh->ncand;
+    for (int i = c.tid; i < c.k; i += c.nthreads) c.out[i] = (i < n) ? c.cand[i] : 0ull;
+}
+
 // MAXT = 256: up to 8 warps, three CTAs per SM (<= 80 registers); MAXT = 512: up to 16 warps, two CTAs per SM
+#ifndef BM25_LB_T
+#define BM25_LB_T 256
+#endif
+#ifndef BM25_LB_B
+#define BM25_LB_B 3
+#endif
 template <int MAXT>
-__global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const SearchArgs a) {
+__global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_score_topk(const SearchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int NCW = blockDim.x >> 5;
-    const int T = a.T, S = a.tile_docs, cap = a.cap;
+    const int T = a.T, S = a.tile_docs;
     float* sc = reinterpret_cast<float*>(smem_raw);
     // candidate buffer: shared memory, or (large k) this CTA's slice of a global, L2-resident array --
     // pushes are rare once the threshold has settled, and the freed shared memory buys a third CTA per SM
     u64* cand_smem = reinterpret_cast<u64*>(sc + (size_t)NCW * S);
-    u64* cand = a.cand_global ? a.cand_global + (size_t)blockIdx.x * cap : cand_smem;
-    int* st_all = reinterpret_cast<int*>(cand_smem + (a.cand_global ? 0 : cap));
+    int* st_all = reinterpret_cast<int*>(cand_smem + (a.cand_global ? 0 : a.cap));
     unsigned short* st_hot = reinterpret_cast<unsigned short*>(st_all + (size_t)NCW * kStateInts * T);
-    __shared__ int s_ncand, s_overflow;
-    __shared__ u64 s_theta;
-    __shared__ int s_hist[264];  // select_candidates scratch
+    __shared__ CtaShared sh;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -600,11 +728,10 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     const int q = blockIdx.x / a.splits;
     const int sp = blockIdx.x - q * a.splits;
     const int chunk = sp * NCW + warp;
-    const WarpsGroup grp{(int)blockDim.x, tid};
 
     if (a.poison) {  // debug: no read of uninitialised shared memory may go unnoticed
         unsigned* all = reinterpret_cast<unsigned*>(smem_raw);
-        const size_t words = ((size_t)NCW * S * 4 + (a.cand_global ? 0 : (size_t)cap * 8) +
+        const size_t words = ((size_t)NCW * S * 4 + (a.cand_global ? 0 : (size_t)a.cap * 8) +
                               (size_t)NCW * kStateInts * T * 4 + (size_t)NCW * kHotCap * 2) / 4;
         for (size_t i = tid; i < words; i += blockDim.x) all[i] = 0xffffffffu;
         __syncthreads();
@@ -612,82 +739,76 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
     float* scw = sc + (size_t)warp * S;
     for (int i = lane * 4; i < S; i += 128) *reinterpret_cast<float4*>(scw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid == 0) {
-        s_ncand = 0;
-        s_overflow = 0;
+        sh.ncand = 0;
+        sh.overflow = 0;
         const u64 shared_theta = a.theta_q ? *reinterpret_cast<volatile u64*>(a.theta_q + q) : 0ull;
-        s_theta = shared_theta > a.theta0 ? shared_theta : a.theta0;
+        sh.theta = shared_theta > a.theta0 ? shared_theta : a.theta0;
     }
     __syncthreads();
 
-    TopkState tk{cand, &s_ncand, &s_overflow, cap, a.general, 0ull, 0.f};
-    tk.set_theta(s_theta);
-    bool leftover = false;       // this warp's tile still holds scores that did not fit in cand
-    uint32_t left_doc0 = 0;
-    int left_nd = 0;
-    HotList hl{st_hot + warp * kHotCap, kHotCap + 1, (1u << lane) - 1u};
-
-    u64* out = a.partial + ((int64_t)q * a.splits + sp) * a.k;  // this CTA's k output keys (also select scratch)
-
-    // candidate-buffer overflow round: every warp of the CTA takes part
-    auto overflow_round = [&]() {
-        for (;;) {
-            if (cap > kSelectMin)  // a round is only entered with a full buffer (n = cap > k)
-                select_candidates(cand, cap, a.k, out, s_hist, &s_ncand, &s_theta, true, grp);
-            else
-                compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
-            if (tid == 0) {
-                s_overflow = 0;
-                if (a.theta_q) {  // share the threshold with the other CTAs of this query
-                    const u64 mine = s_theta;
-                    const u64 old = atomicMax(a.theta_q + q, mine);
-                    if (old > mine) s_theta = old;
-                }
-            }
-            grp.sync();
-            tk.set_theta(s_theta);
-            if (leftover) leftover = __any_sync(kFull, tile_scan(scw, S, left_nd, left_doc0, lane, tk));
-            grp.sync();
-            const int again = ld_volatile(&s_overflow);
-            grp.sync();
-            if (!again) break;
-        }
+    // gathered only where a rare path is entered
+    auto cold_ctx = [&]() {
+        ColdCtx c;
+        c.cand = a.cand_global ? a.cand_global + (size_t)blockIdx.x * a.cap : cand_smem;
+        c.out = a.partial + ((int64_t)q * a.splits + sp) * a.k;
+        c.theta_q = a.theta_q ? a.theta_q + q : nullptr;
+        c.theta0 = a.theta0;
+        c.sh = &sh;
+        c.scw = scw;
+        c.hot = st_hot + warp * kHotCap;
+        c.cap = a.cap;
+        c.k = a.k;
+        c.S = S;
+        c.general = a.general;
+        c.nthreads = (int)blockDim.x;
+        c.tid = tid;
+        return c;
     };
 
     if (chunk < a.n_chunks) {
-        const unsigned T4 = (unsigned)T * 4u;                                            // bytes per state row
-        const unsigned st = smem_u32(st_all + (size_t)warp * kStateInts * T);             // this warp's state
-        const unsigned tile = smem_u32(scw);                                             // this warp's score tile
+        const unsigned T4 = (unsigned)T * 4u;                                 // bytes per state row
+        const unsigned st = smem_u32(st_all + (size_t)warp * kStateInts * T);  // this warp's state
+        const unsigned tile = smem_u32(scw);                                  // this warp's score tile
+        const unsigned hot_s = smem_u32(st_hot + warp * kHotCap);             // this warp's hot list
         const unsigned uS = (unsigned)S;
         const int NB = a.n_tiles;
         const int j0 = chunk * a.tiles_per_chunk;
         const int j1 = min(NB, j0 + a.tiles_per_chunk);
-        const int32_t* seg0 = a.seg + ((int64_t)q * (a.n_chunks + 1) + chunk) * T;
-        for (int t = lane; t < T; t += 32) {
-            const int term = __ldg(a.queries + (int64_t)q * T + t);
-            const bool valid = term >= 0 && term < a.n_terms;
-            const int row = valid ? __ldg(a.term_row + term) : -1;
-            const unsigned s = st + 4u * t;
-            if (row >= 0) {
-                const int32_t* tr = a.tab + (int64_t)row * (NB + 1);
-                sts_i32(s + ((j0 + 0) & 3) * T4, __ldg(tr + j0));
-                sts_i32(s + ((j0 + 1) & 3) * T4, __ldg(tr + min(j0 + 1, NB)));
-                sts_i32(s + ((j0 + 2) & 3) * T4, __ldg(tr + min(j0 + 2, NB)));
-                sts_i32(s + ((j0 + 3) & 3) * T4, 0);
-                sts_i32(s + 4 * T4, row);
-                sts_i32(s + 7 * T4, 1);
-            } else {
-                int p = 0, e = 0;
-                if (valid) {
-                    p = __ldg(seg0 + t);
-                    e = __ldg(seg0 + T + t);
+        const bool hot_enabled = !a.general && !a.no_hot;
+        float theta_f;
+        {
+            const u64 t0 = sh.theta;
+            theta_f = (t0 == 0ull) ? -INFINITY : (a.general ? key_score(t0) : fmaxf(key_score(t0), 1.401298464e-45f));
+        }
+        {
+            const int32_t* seg0 = a.seg + ((int64_t)q * (a.n_chunks + 1) + chunk) * T;
+            for (int t = lane; t < T; t += 32) {
+                const int term = __ldg(a.queries + (int64_t)q * T + t);
+                const bool valid = term >= 0 && term < a.n_terms;
+                const int row = valid ? __ldg(a.term_row + term) : -1;
+                const unsigned s = st + 4u * t;
+                if (row >= 0) {
+                    const int32_t* tr = a.tab + (int64_t)row * (NB + 1);
+                    sts_i32(s + ((j0 + 0) & 3) * T4, __ldg(tr + j0));
+                    sts_i32(s + ((j0 + 1) & 3) * T4, __ldg(tr + min(j0 + 1, NB)));
+                    sts_i32(s + ((j0 + 2) & 3) * T4, __ldg(tr + min(j0 + 2, NB)));
+                    sts_i32(s + ((j0 + 3) & 3) * T4, 0);
+                    sts_i32(s + 4 * T4, row);
+                    sts_i32(s + 7 * T4, 1);
+                } else {
+                    int p = 0, e = 0;
+                    if (valid) {
+                        p = __ldg(seg0 + t);
+                        e = __ldg(seg0 + T + t);
+                    }
+                    sts_i32(s + 0 * T4, p);
+                    sts_i32(s + 1 * T4, e);
+                    sts_i32(s + 2 * T4, p < e ? __ldg(a.ids + p) : kDocNone);
+                    sts_i32(s + 4 * T4, p < e ? __float_as_int(__ldg(a.w + p)) : 0);
+                    sts_i32(s + 3 * T4, p + 1 < e ? __ldg(a.ids + p + 1) : kDocNone);
+                    sts_i32(s + 5 * T4, p + 1 < e ? __float_as_int(__ldg(a.w + p + 1)) : 0);
+                    sts_i32(s + 7 * T4, 0);
                 }
-                sts_i32(s + 0 * T4, p);
-                sts_i32(s + 1 * T4, e);
-                sts_i32(s + 2 * T4, p < e ? __ldg(a.ids + p) : kDocNone);
-                sts_i32(s + 4 * T4, p < e ? __float_as_int(__ldg(a.w + p)) : 0);
-                sts_i32(s + 3 * T4, p + 1 < e ? __ldg(a.ids + p + 1) : kDocNone);
-                sts_i32(s + 5 * T4, p + 1 < e ? __float_as_int(__ldg(a.w + p + 1)) : 0);
-                sts_i32(s + 7 * T4, 0);
             }
         }
         for (int j = j0; j < j1; ++j) {
@@ -697,9 +818,24 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
             const int tile_end = base + S;
             bool touched = false;
             bool refill_inflight = false;  // a light-term refill was requested during THIS tile
-            hl.reset(!a.general && !a.no_hot);
+            int hl_n = hot_enabled ? 0 : kHotCap + 1;  // hot-list length; > kHotCap: overflowed / disabled
             const unsigned r0 = st + (j & 3) * T4, r1 = st + ((j + 1) & 3) * T4, r3 = st + ((j + 3) & 3) * T4;
             const int jn = min(j + 3, NB);
+
+            // warp-collective: append the tile slots of the lanes with `hot` to the hot list
+            auto hot_add = [&](bool hot, int slot) {
+                const unsigned m = __ballot_sync(kFull, hot);
+                if (m == 0u) return;
+                const int c = __popc(m);
+                if (hl_n + c <= kHotCap) {
+                    unsigned lt;
+                    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+                    if (hot) asm volatile("st.shared.u16 [%0], %1;" ::"r"(hot_s + 2u * (hl_n + __popc(m & lt))), "h"((unsigned short)slot) : "memory");
+                    hl_n += c;
+                } else {
+                    hl_n = kHotCap + 1;
+                }
+            };
 
             // light terms of `mask` (bit b = term g0 + b), in query order; lane 0 adds, from the
             // cursor's resident postings
@@ -715,9 +851,9 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
                             const unsigned slot = tile + 4u * (unsigned)(hd - base);
                             const float nw = lds_f32(slot) + __int_as_float(lds_i32(s + 4 * T4));
                             sts_f32(slot, nw);
-                            hot = nw >= tk.theta_f;
+                            hot = nw >= theta_f;
                         }
-                        if (hl.active()) hl.add(hot, hd - base);
+                        if (hl_n <= kHotCap) hot_add(hot, hd - base);
                         if (refill_inflight) {  // the second resident posting may still be on its way
                             cp_async_wait_all();
                             refill_inflight = false;
@@ -787,12 +923,12 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
                     }
                     float n0, n1, n2, n3;
                     P.add_into(tile, base, uS, n0, n1, n2, n3);
-                    if (hl.active()) {  // postings outside the tile give n = 0 < theta_f
-                        if (__any_sync(kFull, fmaxf(fmaxf(n0, n1), fmaxf(n2, n3)) >= tk.theta_f)) {
-                            hl.add(n0 >= tk.theta_f, P.d.x - base);
-                            hl.add(n1 >= tk.theta_f, P.d.y - base);
-                            hl.add(n2 >= tk.theta_f, P.d.z - base);
-                            hl.add(n3 >= tk.theta_f, P.d.w - base);
+                    if (hl_n <= kHotCap) {  // postings outside the tile give n = 0 < theta_f
+                        if (__any_sync(kFull, fmaxf(fmaxf(n0, n1), fmaxf(n2, n3)) >= theta_f)) {
+                            hot_add(n0 >= theta_f, P.d.x - base);
+                            hot_add(n1 >= theta_f, P.d.y - base);
+                            hot_add(n2 >= theta_f, P.d.z - base);
+                            hot_add(n3 >= theta_f, P.d.w - base);
                         }
                     }
                 };
@@ -816,66 +952,24 @@ __global__ void __launch_bounds__(MAXT, MAXT == 256 ? 3 : 2) k_score_topk(const 
                 __syncwarp();
                 if (lm) light_visits(lm, g0);
             }
-            // ---- epilogue: push the documents that beat the k-th best so far, clear the tile ---
-            if (touched || a.general) {
-                const int nd_w = min(S, a.n_docs - base);
-                bool left = false;
-                if (!hl.active()) {
-                    left = tile_scan(scw, S, nd_w, (uint32_t)base, lane, tk);  // reads, tests and zeroes all S slots
-                } else {
-                    __syncwarp();
-                    for (int i0 = 0; i0 < hl.n; i0 += 32) {
-                        const int i = i0 + lane;
-                        const int x = i < hl.n ? (int)hl.slots[i] : -1 - lane;
-                        const unsigned same = __match_any_sync(kFull, x);  // a slot may be listed twice
-                        if (x >= 0 && (__ffs(same) - 1) == lane) {
-                            const float v = lds_f32(tile + 4u * x);
-                            if (v > 0.f) {  // not yet taken by an earlier step of this loop
-                                if (tk.push(v, (uint32_t)(base + x))) sts_f32(tile + 4u * x, 0.f);
-                                else left = true;
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    left = __any_sync(kFull, left);
-                    if (!left) {
+            // ---- end of tile: the common case is a write-only clear ---------------------------
+            const bool cold = a.general || (touched && hl_n != 0) || ld_volatile(&sh.overflow);
+            if (!cold) {
+                if (touched) {
+                    if (a.bulk_clear) {
+                        smem_bulk_zero(tile, uS * 4u);
+                    } else {
                         for (unsigned off = lane * 16u; off < uS * 4u; off += 512u) sts_zero16(tile + off);
                     }
                 }
-                if (__any_sync(kFull, left)) {  // candidate buffer full: the overflow round rescans this tile
-                    leftover = true;
-                    left_doc0 = (uint32_t)base;
-                    left_nd = nd_w;
-                }
-            }
-            if (leftover || ld_volatile(&s_overflow)) {
-                grp.sync();
-                overflow_round();
+            } else {
+                theta_f = tile_finish(cold_ctx(), base, min(S, a.n_docs - base), hl_n,
+                                      (hl_n <= kHotCap && !a.general) ? 1 : 0);
             }
         }
         cp_async_wait_all();  // nothing of this warp may still be in flight towards shared memory
     }
-    for (;;) {  // finished: keep serving overflow rounds until every warp of the CTA is here
-        grp.sync();
-        if (!ld_volatile(&s_overflow)) break;
-        overflow_round();
-    }
-    const int n_end = min(ld_volatile(&s_ncand), cap);
-    if (n_end > kSelectMin && n_end > a.k) {
-        // the k keepers go straight to the output slot, unsorted (k_merge sorts what it loads)
-        select_candidates(cand, n_end, a.k, out, s_hist, &s_ncand, &s_theta, false, grp);
-        if (tid == 0 && a.theta_q) atomicMax(a.theta_q + q, s_theta);
-        return;
-    }
-    if (a.cand_global) {
-        // here n_end <= k (a larger set went through the select above): everything is a keeper, unsorted
-        for (int i = tid; i < a.k; i += blockDim.x) out[i] = (i < n_end) ? cand[i] : 0ull;
-        return;
-    }
-    compact_candidates(cand, cap, a.k, a.theta0, &s_ncand, &s_theta, grp);
-    if (tid == 0 && a.theta_q && s_ncand >= a.k) atomicMax(a.theta_q + q, s_theta);
-    const int n = s_ncand;
-    for (int i = tid; i < a.k; i += blockDim.x) out[i] = (i < n) ? cand[i] : 0ull;
+    cta_finish(cold_ctx(), a.cand_global != nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
