@@ -166,7 +166,7 @@ struct bm25_index {
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
     int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_heavy_min = 0, opt_cand_smem = 0;
-    int opt_poison = 0, opt_no_bulk_clear = 0;
+    int opt_poison = 0, opt_no_bulk_clear = 0, opt_no_query_sort = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace: one per handle; searches on different streams are ordered through ws_done
@@ -175,7 +175,8 @@ struct bm25_index {
     cudaStream_t ws_stream = nullptr;
     bool ws_used = false;
     DevBuf<int32_t> ws_seg;
-    DevBuf<u64> ws_partial, ws_theta, ws_cand;
+    DevBuf<u64> ws_partial, ws_theta, ws_cand, ws_qkey;
+    DevBuf<int32_t> ws_qperm;
     DevBuf<int32_t> ws_queries, ws_out_ids;
     DevBuf<float> ws_out_scores;
     PinnedBuf<int32_t> pin_queries, pin_out_ids;
@@ -194,7 +195,7 @@ struct bm25_index {
     int64_t device_bytes() const {
         int64_t b = n_terms * 12 + nnz_padded * 8 + tab_bytes;
         if (d_bounds) b += n_terms * kBoundLevels * 4;
-        b += ws_seg.bytes() + ws_partial.bytes() + ws_theta.bytes() + ws_cand.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
+        b += ws_seg.bytes() + ws_partial.bytes() + ws_theta.bytes() + ws_cand.bytes() + ws_qkey.bytes() + ws_qperm.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
              ws_out_scores.bytes();
         return b;
     }
@@ -550,6 +551,17 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
         CU(cudaEventRecord(ix->ev[0], st));
     }
     if ((rc = launch_segments(ix, lp, d_queries, Q, T, k, ix->opt_no_theta_share ? nullptr : ix->ws_theta.p, false, st))) return rc;
+    // cross-query L2 sharing: CTAs of queries with the same heaviest term become neighbours
+    const bool qsort = !ix->opt_no_query_sort && Q > 1 && Q <= (1 << 20);
+    if (qsort) {
+        const int P = next_pow2(Q);
+        if ((rc = ix->ws_qperm.reserve((size_t)Q))) return rc;
+        if (P > 4096 && (rc = ix->ws_qkey.reserve((size_t)P))) return rc;
+        k_query_order<<<1, 1024, P <= 4096 ? (size_t)P * 8 : 0, st>>>(ix->d_tptr, d_queries, (int)Q, (int)T,
+                                                                      (int)ix->n_terms, P, ix->ws_qkey.p, ix->ws_qperm.p);
+        ++g_launches;
+        CU(cudaGetLastError());
+    }
     if (timing) CU(cudaEventRecord(ix->ev[1], st));
     SearchArgs a{};
     a.ids = ix->d_ids;
@@ -557,6 +569,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.term_row = ix->d_term_row;
     a.tab = ix->d_tab;
     a.queries = d_queries;
+    a.qperm = qsort ? ix->ws_qperm.p : nullptr;
     a.seg = ix->ws_seg.p;
     a.partial = ix->ws_partial.p;
     a.theta_q = ix->opt_no_theta_share ? nullptr : ix->ws_theta.p;
@@ -772,6 +785,8 @@ int bm25_index_destroy(bm25_index* ix) {
         ix->ws_partial.release();
         ix->ws_theta.release();
         ix->ws_cand.release();
+        ix->ws_qkey.release();
+        ix->ws_qperm.release();
         ix->ws_queries.release();
         ix->ws_out_ids.release();
         ix->ws_out_scores.release();
@@ -827,6 +842,8 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
     } else if (!strcmp(name, "heavy_min")) {
         if (value < 0 || value > (1 << 28)) return fail(BM25_ERR_INVALID, "heavy_min out of range");
         ix->opt_heavy_min = (int)value;
+    } else if (!strcmp(name, "no_query_sort")) {
+        ix->opt_no_query_sort = value ? 1 : 0;
     } else if (!strcmp(name, "no_bulk_clear")) {
         ix->opt_no_bulk_clear = value ? 1 : 0;
     } else if (!strcmp(name, "poison")) {

@@ -312,12 +312,59 @@ __device__ __forceinline__ void select_candidates(u64* cand, int n, int k, u64* 
     g.sync();
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_query_order: cross-query sharing of posting lists through the L2.  Queries whose heaviest
+// (largest-df) term is the same are given neighbouring CTA indices, so that they are resident at
+// the same time and walk that term's posting list together: the second and later readers of a
+// list segment hit the 126 MB L2 instead of HBM (batched scoring as a sparse query-by-term times
+// term-by-doc product, reference bm25_native.py:160-192, without changing the per-query sums).
+// One CTA; key = (heaviest term id << 32 | query); bitonic sort in shared memory (P <= 4096) or
+// in global memory; perm[i] = query run by the i-th group of CTAs.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_query_order(const int2* __restrict__ tptr, const int32_t* __restrict__ queries,
+                                                      int Q, int T, int n_terms, int P, u64* __restrict__ keys_g,
+                                                      int32_t* __restrict__ perm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* keys = (P <= 4096) ? reinterpret_cast<u64*>(smem_raw) : keys_g;
+    const int tid = threadIdx.x;
+    for (int q = tid; q < P; q += 1024) {
+        u64 key = ~0ull;
+        if (q < Q) {
+            int best = 0x7fffffff, best_df = -1;
+            for (int t = 0; t < T; ++t) {
+                const int term = queries[(int64_t)q * T + t];
+                if (term < 0 || term >= n_terms) continue;
+                const int2 se = tptr[term];
+                const int df = se.y - se.x;
+                if (df > best_df || (df == best_df && term < best)) { best_df = df; best = term; }
+            }
+            key = ((u64)(uint32_t)best << 32) | (uint32_t)q;
+        }
+        keys[q] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < (P >> 1); i += 1024) {
+                const int a = 2 * i - (i & (stride - 1));
+                const int b = a + stride;
+                const bool asc = ((a & size) == 0);
+                const u64 x = keys[a], y = keys[b];
+                if ((x > y) == asc) { keys[a] = y; keys[b] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < Q; i += 1024) perm[i] = (int32_t)(uint32_t)keys[i];
+}
+
 struct SearchArgs {
     const int32_t* __restrict__ ids;       // [nnz_padded] doc ids (padded layout, see above)
     const float* __restrict__ w;           // [nnz_padded] weights
     const int32_t* __restrict__ term_row;  // [V] tile-table row of a heavy term, -1 for a light term
     const int32_t* __restrict__ tab;       // [n_heavy, n_tiles+1] tile table
     const int32_t* __restrict__ queries;   // [Q,T]
+    const int32_t* __restrict__ qperm;     // [Q] query run by each group of `splits` CTAs (k_query_order), or NULL
     const int32_t* __restrict__ seg;       // [Q,n_chunks+1,T] cursor starts of the light terms (k_scores_dense: [Q,n_tiles+1,T], all terms)
     u64* __restrict__ partial;             // [Q,splits,k] keys (0 = none)
     u64* theta_q;                          // [Q] best known k-th key per query (shared by its CTAs)
@@ -725,8 +772,9 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int q = blockIdx.x / a.splits;
-    const int sp = blockIdx.x - q * a.splits;
+    const int qslot = blockIdx.x / a.splits;
+    const int sp = blockIdx.x - qslot * a.splits;
+    const int q = a.qperm ? __ldg(a.qperm + qslot) : qslot;
     const int chunk = sp * NCW + warp;
 
     if (a.poison) {  // debug: no read of uninitialised shared memory may go unnoticed
@@ -749,7 +797,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
     // gathered only where a rare path is entered
     auto cold_ctx = [&]() {
         ColdCtx c;
-        c.cand = a.cand_global ? a.cand_global + (size_t)blockIdx.x * a.cap : cand_smem;
+        c.cand = a.cand_global ? a.cand_global + ((size_t)q * a.splits + sp) * a.cap : cand_smem;
         c.out = a.partial + ((int64_t)q * a.splits + sp) * a.k;
         c.theta_q = a.theta_q ? a.theta_q + q : nullptr;
         c.theta0 = a.theta0;
