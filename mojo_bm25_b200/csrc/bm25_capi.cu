@@ -623,7 +623,9 @@ int check_search_args(const bm25_index* ix, int64_t Q, int64_t T, int k) {
     if (k < 1) return fail(BM25_ERR_INVALID, "k must be >= 1 (got %d)", k);
     if (k > ix->n_docs)
         return fail(BM25_ERR_INVALID, "kth(=-%d) out of bounds (%lld)", k, (long long)ix->n_docs);
-    if (k > BM25_MAX_K) return fail(BM25_ERR_UNSUPPORTED, "k=%d exceeds BM25_MAX_K=%d", k, BM25_MAX_K);
+    if (k > BM25_MAX_K)
+        return fail(BM25_ERR_INVALID, "k=%d exceeds BM25_MAX_K=%d, the largest top-k this build selects on the device", k,
+                    BM25_MAX_K);
     return BM25_OK;
 }
 

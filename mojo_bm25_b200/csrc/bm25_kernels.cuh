@@ -607,19 +607,25 @@ struct PostingPiece {
     }
 };
 
-// vectorised scan + zero of one warp's tile (S documents, the first nd_w of them real)
+// Vectorised scan of one warp's tile (S documents, the first nd_w of them real): pushes every
+// document that beats the threshold and marks its slot as done; a slot whose push did not fit into
+// the candidate buffer keeps its score for the rescan of the next overflow round (returns true).
+// Positive path: done = 0.0 (never competitive, theta_f > 0), so a clean scan leaves the tile zeroed.
+// General path (zero and negative scores compete): done = -inf, which no rescan pushes again; the
+// caller zeroes the tile once the scan is clean (tile_clear).
 __device__ __forceinline__ bool tile_scan(float* scw, int S, int nd_w, uint32_t doc0, int lane, TopkState& tk) {
     bool left = false;
+    const float done = tk.general ? -INFINITY : 0.f;
 #pragma unroll 4
     for (int idx = lane * 4; idx < S; idx += 128) {
         const float4 v = *reinterpret_cast<const float4*>(scw + idx);
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 z = make_float4(done, done, done, done);
         if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= tk.theta_f) {
             const float vv[4] = {v.x, v.y, v.z, v.w};
-            float zz[4] = {0.f, 0.f, 0.f, 0.f};
+            float zz[4] = {done, done, done, done};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                if (vv[e] >= tk.theta_f && idx + e < nd_w) {
+                if (vv[e] >= tk.theta_f && vv[e] != -INFINITY && idx + e < nd_w) {
                     if (!tk.push(vv[e], doc0 + (uint32_t)(idx + e))) { zz[e] = vv[e]; left = true; }
                 }
             }
@@ -628,6 +634,9 @@ __device__ __forceinline__ bool tile_scan(float* scw, int S, int nd_w, uint32_t 
         *reinterpret_cast<float4*>(scw + idx) = z;
     }
     return left;
+}
+__device__ __forceinline__ void tile_clear(float* scw, int S, int lane) {
+    for (int idx = lane * 4; idx < S; idx += 128) *reinterpret_cast<float4*>(scw + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -672,7 +681,10 @@ __device__ __forceinline__ void overflow_round(const ColdCtx& c, TopkState& tk, 
         }
         grp.sync();
         tk.set_theta(c.sh->theta);
-        if (leftover) leftover = __any_sync(kFull, tile_scan(c.scw, c.S, left_nd, left_doc0, lane, tk));
+        if (leftover) {
+            leftover = __any_sync(kFull, tile_scan(c.scw, c.S, left_nd, left_doc0, lane, tk));
+            if (!leftover && c.general) tile_clear(c.scw, c.S, lane);  // the scan left -inf marks
+        }
         grp.sync();
         const int again = ld_volatile(&c.sh->overflow);
         grp.sync();
@@ -690,7 +702,8 @@ __device__ __noinline__ float tile_finish(const ColdCtx c, int base, int nd_w, i
     tk.set_theta(c.sh->theta);  // thresholds only change inside rounds, which every warp attends
     bool left = false;
     if (!use_list) {
-        left = tile_scan(c.scw, c.S, nd_w, (uint32_t)base, lane, tk);  // reads, tests and zeroes all S slots
+        left = __any_sync(kFull, tile_scan(c.scw, c.S, nd_w, (uint32_t)base, lane, tk));  // reads and tests all S slots
+        if (!left && c.general) tile_clear(c.scw, c.S, lane);
     } else {
         __syncwarp();
         for (int i0 = 0; i0 < hl_n; i0 += 32) {
@@ -707,9 +720,7 @@ __device__ __noinline__ float tile_finish(const ColdCtx c, int base, int nd_w, i
             __syncwarp();
         }
         left = __any_sync(kFull, left);
-        if (!left)
-            for (int idx = lane * 4; idx < c.S; idx += 128)
-                *reinterpret_cast<float4*>(c.scw + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!left) tile_clear(c.scw, c.S, lane);
     }
     left = __any_sync(kFull, left);
     if (left || ld_volatile(&c.sh->overflow)) {

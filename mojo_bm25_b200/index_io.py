@@ -31,7 +31,7 @@ class DiskIndex:
     data: np.ndarray
     vocab: Dict[str, int]
     params: dict
-    corpus: Optional[List] = None
+    corpus: Optional[object] = None  # JsonlCorpus (offset-indexed) or a list
     corpus_offsets: List[int] = field(default_factory=list)
 
     @property
@@ -41,6 +41,49 @@ class DiskIndex:
     @property
     def num_terms(self) -> int:
         return int(self.indptr.shape[0] - 1)
+
+
+class JsonlCorpus:
+    """The documents of ``corpus.jsonl`` fetched by byte offset: ``corpus.mmindex.json`` holds the
+    offset of every line ([0, 57, 129, 192] in the bundled index), so returning the documents of
+    a top-k costs one seek + one line read each instead of parsing the whole file (what bm25s'
+    ``load_corpus=True, mmap=True`` does with the same two files)."""
+
+    def __init__(self, path: str, offsets: List[int]):
+        self.path = path
+        self.offsets = [int(o) for o in offsets]
+        self._f = None
+
+    def __len__(self) -> int:
+        return len(self.offsets)
+
+    def _file(self):
+        if self._f is None:
+            self._f = open(self.path, "rb")
+        return self._f
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        i = int(i)
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        f = self._file()
+        f.seek(self.offsets[i])
+        return json.loads(f.readline())
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+    def close(self):
+        if self._f is not None:
+            self._f.close()
+            self._f = None
+
+    def __del__(self):
+        self.close()
 
 
 def validate(indptr, indices, data, num_docs: int) -> None:
@@ -73,14 +116,17 @@ def load_index(path: str, load_corpus: bool = False, mmap: bool = False) -> Disk
     validate(indptr, indices, data, int(params["num_docs"]))
     corpus, offsets = None, []
     if load_corpus and os.path.exists(os.path.join(path, CORPUS)):
-        corpus = []
-        with open(os.path.join(path, CORPUS), "rb") as f:
-            for line in f:
-                if line.strip():
-                    corpus.append(json.loads(line))
         idx_path = os.path.join(path, CORPUS_INDEX)
         if os.path.exists(idx_path):
-            offsets = json.load(open(idx_path))
+            with open(idx_path) as f:
+                offsets = json.load(f)
+            corpus = JsonlCorpus(os.path.join(path, CORPUS), offsets)  # documents are fetched by offset
+        else:  # no offset index: parse the whole file
+            corpus = []
+            with open(os.path.join(path, CORPUS), "rb") as f:
+                for line in f:
+                    if line.strip():
+                        corpus.append(json.loads(line))
     return DiskIndex(indptr, indices, data, vocab, params, corpus, offsets)
 
 

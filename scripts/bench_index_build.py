@@ -11,6 +11,8 @@ import numpy as np
 import torch
 
 from mojo_bm25_b200 import index_build
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from _index_build_ref import build_csc_reference_numpy
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--docs", type=int, default=1_000_000)
@@ -35,7 +37,7 @@ gpu_s = time.perf_counter() - t0
 nc = int(ptr[a.cpu_docs])
 tok_h, ptr_h = tok[:nc].cpu().numpy(), ptr[: a.cpu_docs + 1].cpu().numpy()
 t0 = time.perf_counter()
-ref = index_build.build_csc_reference_numpy(tok_h, ptr_h, a.terms)
+ref = build_csc_reference_numpy(tok_h, ptr_h, a.terms)
 cpu_s = time.perf_counter() - t0
 print(json.dumps({"metric": "index build tokens/s", "gpu_tokens_per_s": n_tok / gpu_s, "gpu_seconds": gpu_s,
                   "tokens": n_tok, "docs": a.docs, "postings": int(out[1].numel()),

@@ -1,10 +1,16 @@
 """Index builder: the torch pipeline (run here on the CPU device, on
-CUDA under -m gpu) against its numpy restatement and against the dense drop-in's host ``fit``."""
+CUDA under -m gpu) against its numpy restatement (tests/_index_build_ref.py), against the oracle's
+``OracleBM25.fit`` (bm25.py:30-121) and against the reference's bundled bm25s index
+(animal_index_bm25/, written by bm25_test.py:19-38)."""
+import filecmp
+import os
+
 import numpy as np
 import pytest
 import torch
 
-from mojo_bm25_b200 import index_build
+from mojo_bm25_b200 import index_build, index_io
+from _index_build_ref import build_csc_reference_numpy
 
 FOX = ["the quick brown fox jumps over the lazy dog", "a quick brown dog outpaces a lazy fox",
        "the lazy dog sleeps", "tall trees in the forest", "the forest has tall tall trees and a fox", ""]
@@ -31,7 +37,7 @@ def test_builder_matches_numpy_bitwise_on_cpu(variant):
     for n_docs, n_terms, mean_len in [(1, 3, 4), (50, 20, 6), (400, 300, 30)]:
         flat, ptr = index_build.flatten_corpus(_random_corpus(rng, n_docs, n_terms, mean_len))
         got = index_build.build_csc(flat, ptr, n_terms, variant=variant, device="cpu")
-        want = index_build.build_csc_reference_numpy(flat, ptr, n_terms, variant=variant)
+        want = build_csc_reference_numpy(flat, ptr, n_terms, variant=variant)
         _same(got, want)
         indptr, indices = want[0], want[1]
         assert indptr[-1] == len(indices)
@@ -48,7 +54,7 @@ def test_bm25py_variant_equals_the_dense_dropins_fit():
     flat, ptr = index_build.flatten_corpus([[tid[t] for t in d] for d in docs])
     got = index_build.build_csc(flat, ptr, len(vocab), variant="bm25py", device="cpu")
     # the same arithmetic as mojo_bm25_b200/bm25.py::BM25.fit, restated without a device
-    want = index_build.build_csc_reference_numpy(flat, ptr, len(vocab), variant="bm25py")
+    want = build_csc_reference_numpy(flat, ptr, len(vocab), variant="bm25py")
     _same(got, want)
     from oracle import bm25_oracle as orc
 
@@ -59,6 +65,76 @@ def test_bm25py_variant_equals_the_dense_dropins_fit():
     cols = np.repeat(np.arange(len(vocab)), np.diff(indptr))
     dense[indices, cols] = data
     np.testing.assert_allclose(dense, np.asarray(o.bm25_matrix), rtol=1e-6, atol=0)
+
+
+def _bundled_corpus_ids(golden_dir):
+    """The stemmed token ids of the reference's 4-document animal corpus, recovered from the bundled
+    index itself: every posting has tf = 1 (doc lengths 4, 6, 5, 5 = the row counts)."""
+    d = index_io.load_index(os.path.join(golden_dir, "animal_index_bm25"), load_corpus=True)
+    cols = np.repeat(np.arange(d.num_terms), np.diff(d.indptr))
+    docs = [sorted(cols[d.indices == doc].tolist()) for doc in range(d.num_docs)]
+    assert [len(x) for x in docs] == [4, 6, 5, 5]
+    return d, docs
+
+
+def _check_bundled_reproduction(golden_dir, tmp_path, device):
+    d, docs = _bundled_corpus_ids(golden_dir)
+    flat, ptr = index_build.flatten_corpus(docs)
+    indptr, indices, data, dl = index_build.build_csc(flat, ptr, d.num_terms, variant="lucene", device=device)
+    assert np.array_equal(indptr.cpu().numpy(), d.indptr) and np.array_equal(indices.cpu().numpy(), d.indices)
+    # the 20 floats bm25s 0.2.12 wrote (data.csc.index.npy); bm25s computes in float32, the builder in
+    # float64 then rounds: at most 1 ulp apart
+    np.testing.assert_allclose(data.cpu().numpy(), d.data, rtol=2e-7, atol=0)
+    assert dl.cpu().numpy().tolist() == [4, 6, 5, 5]
+    # written back in the on-disk layout with the bundled weights: the same seven files, byte for byte
+    index_io.save_index(str(tmp_path), indptr.cpu().numpy(), indices.cpu().numpy(), d.data, d.vocab, d.num_docs,
+                        corpus=d.corpus)
+    src = os.path.join(golden_dir, "animal_index_bm25")
+    for f in sorted(os.listdir(src)):
+        assert filecmp.cmp(os.path.join(src, f), os.path.join(str(tmp_path), f), shallow=False), f
+    return data.cpu().numpy(), d
+
+
+def test_builder_reproduces_the_bundled_bm25s_index_on_cpu(golden_dir, tmp_path):
+    _check_bundled_reproduction(golden_dir, tmp_path, "cpu")
+
+
+def _check_against_oracle_fit(device):
+    """bm25.py:30-121 through the oracle: whitespace tokens, sorted vocabulary, (k1+1) numerator."""
+    from oracle import bm25_oracle as orc
+
+    rng = np.random.default_rng(5)
+    words = [f"w{i}" for i in range(60)]
+    docs = [[words[j] for j in rng.choice(60, size=int(rng.integers(1, 14)), p=(1 / np.arange(1, 61)) / np.sum(1 / np.arange(1, 61)))]
+            for _ in range(80)]
+    o = orc.OracleBM25()
+    o.fit(docs)
+    vocab = sorted({t for doc in docs for t in doc})
+    tid = {t: i for i, t in enumerate(vocab)}
+    flat, ptr = index_build.flatten_corpus([[tid[t] for t in doc] for doc in docs])
+    indptr, indices, data, _ = (x.cpu().numpy() for x in index_build.build_csc(flat, ptr, len(vocab), variant="bm25py", device=device))
+    dense = np.zeros((len(docs), len(vocab)), dtype=np.float64)
+    dense[indices, np.repeat(np.arange(len(vocab)), np.diff(indptr))] = data
+    ref = np.asarray(o.bm25_matrix)
+    assert np.array_equal(dense != 0, ref != 0)
+    np.testing.assert_allclose(dense, ref, rtol=1e-6, atol=0)  # float32 storage of float64 weights
+
+
+def test_builder_matches_oracle_fit_on_cpu():
+    _check_against_oracle_fit("cpu")
+
+
+@pytest.mark.gpu
+def test_builder_on_gpu_matches_oracle_fit_and_the_bundled_index(golden_dir, tmp_path):
+    _check_against_oracle_fit("cuda")
+    data, d = _check_bundled_reproduction(golden_dir, tmp_path, "cuda")
+    # and the built index answers the reference's known query G1 like the bundled one
+    from mojo_bm25_b200.bm25s_api import BM25
+
+    r = BM25.from_arrays(d.indptr, d.indices, data, d.num_docs, vocab=d.vocab)
+    res = r.retrieve([["fish", "purr", "cat", "like"]], k=2)
+    assert res.documents.tolist() == [[0, 3]]
+    np.testing.assert_allclose(res.scores, [[1.5876564, 0.48158914]], rtol=1e-6)
 
 
 def test_empty_inputs():
@@ -77,7 +153,7 @@ def test_builder_on_gpu_and_bm25s_shaped_index_roundtrip(tmp_path):
     corpus = _random_corpus(rng, 3000, 500, 25)
     flat, ptr = index_build.flatten_corpus(corpus)
     got = index_build.build_csc(flat, ptr, 500, variant="lucene", device="cuda")
-    want = index_build.build_csc_reference_numpy(flat, ptr, 500, variant="lucene")
+    want = build_csc_reference_numpy(flat, ptr, 500, variant="lucene")
     _same(got, want)
     r = BM25()
     r.index(corpus, n_terms=500)

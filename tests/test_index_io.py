@@ -21,6 +21,31 @@ def test_load_bundled_index(golden_dir):
     assert d.data.view(np.uint32).tolist() == g["data_bits"]
 
 
+def test_documents_are_fetched_through_the_offset_index(golden_dir, tmp_path):
+    """corpus.mmindex.json is used to seek: a document is readable even when every OTHER line of
+    corpus.jsonl is unparsable, and only the requested bytes are touched."""
+    import shutil
+
+    src = os.path.join(golden_dir, "animal_index_bm25")
+    dst = str(tmp_path / "idx")
+    shutil.copytree(src, dst)
+    raw = open(os.path.join(dst, "corpus.jsonl"), "rb").read()
+    offs = json.load(open(os.path.join(dst, "corpus.mmindex.json")))
+    assert offs == [0, 57, 129, 192]
+    broken = bytearray(raw)
+    for i in range(offs[1], offs[3] - 1):  # wreck documents 1 and 2, keep their length (and newlines)
+        if broken[i] != 0x0A:
+            broken[i] = ord("#")
+    open(os.path.join(dst, "corpus.jsonl"), "wb").write(bytes(broken))
+    d = index_io.load_index(dst, load_corpus=True)
+    assert isinstance(d.corpus, index_io.JsonlCorpus) and len(d.corpus) == 4
+    assert d.corpus[3]["text"].startswith("a fish") and d.corpus[0]["id"] == 0 and d.corpus[-1]["id"] == 3
+    with pytest.raises(ValueError):
+        d.corpus[1]
+    whole = index_io.load_index(src, load_corpus=True)
+    assert [doc["id"] for doc in whole.corpus] == [0, 1, 2, 3] and whole.corpus[1:3][1]["id"] == 2
+
+
 def test_writer_is_byte_exact(golden_dir, tmp_path):
     src = os.path.join(golden_dir, "animal_index_bm25")
     d = index_io.load_index(src, load_corpus=True)

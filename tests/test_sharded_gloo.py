@@ -113,3 +113,35 @@ def test_doc_ranges_cover_corpus():
         spans = [sharded.doc_range_of_rank(n, w, r) for r in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_short_and_empty_tail_shards_single_process():
+    """A tail shard with fewer than k documents (or none) is searched with k_local = its size and
+    padded with (id -1, score -inf) entries that the merge ignores (host logic, oracle injected)."""
+    from mojo_bm25_b200 import sharded
+
+    indptr, indices, data, n_docs, q = _make_case()
+    keep = indices < 13  # a 13-document corpus cut into ceil(13/4) = 4-document ranges: 4, 4, 4, 1
+    col_of = np.repeat(np.arange(len(indptr) - 1), np.diff(indptr))
+    ptr = np.zeros(len(indptr), np.int32)
+    np.cumsum(np.bincount(col_of[keep], minlength=len(indptr) - 1), out=ptr[1:])
+    ind, dat = indices[keep], data[keep]
+    for n_shards, k in [(4, 4), (4, 13), (7, 5)]:
+        parts = orc.partition_csc_by_doc_range(ptr, ind, dat, 13, n_shards)
+
+        def make(part):
+            p, i_, d, nd, base = part
+
+            def local(queries, kk, out_ids, out_scores):
+                assert 0 < kk <= nd
+                i, s = orc.search_csc(p, i_, d, nd, queries.numpy(), kk)
+                out_ids.copy_(torch.from_numpy(i + base))
+                out_scores.copy_(torch.from_numpy(s))
+
+            return local
+
+        s = sharded.DocShardedSearcher([make(p) for p in parts], k, merge=_oracle_merge, shard_docs=[p[3] for p in parts])
+        ids, sc = s.search(torch.from_numpy(q))
+        for i in range(len(q)):
+            dense = orc.scores_dense(ptr, ind, dat, 13, q[i])
+            orc.check_topk_against_dense(ids[i].numpy(), sc[i].numpy(), dense, k, exact=True)
