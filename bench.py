@@ -2,14 +2,24 @@
 """bench.py -- BM25 query hot-path benchmark (contract: see DESIGN.md "Measurement").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload B|C|10M|D|E|tiny]
-                    [--mode auto|query-split|doc-shard] [--impl ours|reference]
+                    [--mode auto|query-split|doc-shard] [--impl ours|reference] [--no-subrecords]
 
-A *step* is one pass of the hot path (segment table -> score accumulation + per-range top-k ->
-merge) over one batch of synthetic queries.  Default workload = BASELINE.json configs[1] ("B":
-1M docs, 100k-term Zipf vocabulary, 1000 queries x 4 terms, top-10).  One JSON line is printed by
-rank 0.  `value` = whole-job queries/s with the index and the queries resident in HBM (CUDA-event
-timed, L2 flushed between steps); `e2e` = the same metric through the host-buffer C-ABI call
-(bm25_search_host: pinned H2D of the queries, kernels, D2H of ids+scores, every step).
+A *step* is one pass of the hot path (threshold priming + cursor starts -> query ordering -> score
+accumulation + per-range top-k -> merge) over one batch of synthetic queries.  Default workload =
+BASELINE.json configs[1] ("B": 1M docs, 100k-term Zipf vocabulary, 1000 queries x 4 terms, top-10).
+Rank 0 prints ONE JSON line.  `value` = whole-job queries/s with the index and the queries
+resident in HBM (CUDA-event timed, L2 flushed between steps); `e2e` = the same metric through the
+host-buffer C-ABI call (bm25_search_host: pinned H2D of the queries, kernels, D2H of ids+scores,
+every step).  The same line carries sub-records measured in the same run so that the whole
+BASELINE metric is on it:
+
+    k100      workload B at k = 100
+    wE        config E (1M docs, 1000 x 64 terms incl. stop-word-length lists, k = 1000)
+    w10M      the 10M-document target index of north_star (1000 x 6 terms, k = 100), own roofline
+    wC        config C (8.8M passages, 10k queries x ~6 terms, k = 100)           [N = 1 only]
+    doc_shard config D: 100M documents as 8 document-range shards spread over the N GPUs (all 8 on
+              one GPU at N = 1), local top-k + NCCL all-gather + merge kernel; strong scaling;
+              local / all-gather / merge device ms and an oracle parity check of a query sample
 """
 from __future__ import annotations
 
@@ -43,7 +53,9 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only)")
     ap.add_argument("--k", type=int, default=0, help="override top-k (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-subrecords", action="store_true", help="only the headline workload")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the CPU baseline sample")
+    ap.add_argument("--doc-shard-scale", type=float, default=1.0, help="shrink config D (debug only)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     return a
@@ -69,12 +81,12 @@ def load_peaks():
 
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clock + throttle reasons of one GPU during the timed region (NVML thread)."""
+    """Samples SM clock + throttle reasons of one GPU during the timed regions (NVML thread)."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
 
-    def __init__(self, torch_device_index: int, period_s: float = 0.02):
+    def __init__(self, torch_device_index: int, period_s: float = 0.005):
         self.period = period_s
         self.samples, self.reason_bits, self.max_mhz = [], 0, None
         self._stop = threading.Event()
@@ -160,19 +172,40 @@ def cpu_sample_size(n_queries, n_docs, cores, override=0):
     return max(cores, min(n_queries, n, 64 * cores))
 
 
-def workload_config(args, wl_cfg, idx, queries, k, extra=None):
+def parallelism(mode, world, n_q, n_docs=0, total_shards=1, k=0):
+    if mode == "single":
+        return "1 GPU"
+    if mode == "query-split":
+        return (f"query-split x{world}: index replicated, each rank answers its own {n_q}-query batch, "
+                "no data-path collective")
+    per_rank = total_shards // world
+    return (f"doc-shard x{world}: {total_shards} shards of {n_docs} docs ({n_docs * total_shards} total), "
+            f"{per_rank} per rank, same batch on every rank, local top-k + NCCL all-gather of "
+            f"{n_q * k * 8 * per_rank} B per rank + merge kernel")
+
+
+def headline_mode(args, world):
+    mode = args.mode
+    if mode == "auto":
+        mode = "query-split" if world > 1 and args.workload != "D" else ("doc-shard" if world > 1 else "single")
+    if args.workload == "D" and mode != "query-split":
+        return "doc-shard"  # the 100M-doc corpus only exists as 8 document shards, also on one GPU
+    if world == 1:
+        return "single"
+    return mode
+
+
+def workload_config(args, wl_name, n_docs, n_terms, nnz, n_q, width, k, r0, mode, world, total_shards):
     cfg = {
-        "workload": f"{args.workload}: synthetic saturating-Zipf CSC index, {idx.n_docs} docs, {idx.n_terms} terms, "
-                    f"nnz={idx.nnz}; {queries.shape[0]} queries x {queries.shape[1]} term slots (r0={wl_cfg.get('r0', 8)}), "
-                    f"top-{k}",
-        "n_docs": idx.n_docs, "n_terms": idx.n_terms, "nnz": idx.nnz, "n_queries": int(queries.shape[0]),
-        "query_width": int(queries.shape[1]), "k": int(k), "index_seed": 0, "query_seed": 1,
+        "workload": f"{wl_name}: synthetic saturating-Zipf CSC index, {n_docs} docs, {n_terms} terms, "
+                    f"nnz={nnz}; {n_q} queries x {width} term slots (r0={r0}), top-{k}",
+        "n_docs": n_docs, "n_terms": n_terms, "nnz": nnz, "n_queries": n_q,
+        "query_width": width, "k": int(k), "index_seed": 0, "query_seed": 1,
         "cache": "L2 flushed (256 MiB memset) between timed steps; index is larger than L2",
+        "parallelism": parallelism(mode, world, n_q, n_docs, total_shards, k), "shards": total_shards,
     }
     if args.scale != 1.0:
         cfg["scale"] = args.scale
-    if extra:
-        cfg.update(extra)
     return cfg
 
 
@@ -204,11 +237,15 @@ def run_reference(args):
     res = run_cpu_port(indptr, indices, data, idx.n_docs, qn[:n_sample], k, args.steps, args.warmup)
     qps = res["qps"]
     sample = f"first {n_sample} of {len(qn)} queries per step, {res['cores']} forked workers"
+    mode = headline_mode(args, args.gpus)
+    total_shards = (8 if args.workload == "D" else args.gpus) if mode == "doc-shard" else 1
     line = {
         "impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(res["step_seconds"])), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
-        "config": workload_config(args, wl_cfg, idx, q, k),
+        "scaling": "strong" if (mode == "doc-shard" and args.workload == "D") else "weak", "vs_baseline": None,
+        "dtype": DTYPE, "data": "synthetic",
+        "config": workload_config(args, args.workload, idx.n_docs, idx.n_terms, idx.nnz, int(q.shape[0]),
+                                  int(q.shape[1]), k, wl_cfg.get("r0", 8), mode, args.gpus, total_shards),
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -217,214 +254,369 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------
-def run_ours(args):
+class Ctx:
+    """Per-process benchmark context: device, distributed handles, L2 flush buffer, peaks."""
+
+    def __init__(self, args):
+        import torch
+
+        self.args = args
+        self.rank, self.world, self.local = dist_env()
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.peak, self.peak_src = load_peaks()
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def max_over_ranks(self, x: float) -> float:
+        import torch
+
+        if self.dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def timed_steps(ctx, step, steps, warmup):
+    """W untimed steps, then EXACTLY `steps` steps, each bracketed by CUDA events on the launching
+    stream with the L2 flushed in between (the flush is outside the events); barrier + synchronize
+    on both sides; returns (per-step ms list of this rank, MAX-over-ranks mean ms per step, wall s)."""
+    import torch
+
+    for _ in range(warmup):
+        ctx.flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ctx.barrier()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(steps):
+        ctx.flush.zero_()
+        starts[i].record()
+        step()
+        ends[i].record()
+    torch.cuda.synchronize()
+    ctx.barrier()
+    wall = time.perf_counter() - wall0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    return step_ms, ctx.max_over_ranks(float(sum(step_ms))) / steps, wall
+
+
+def kernel_split(ctx, indexes, step, steps):
+    """Second, separate pass (its waits are NOT inside the timed loop of `value`): per-kernel device
+    time from the library's own events on the launching stream -> mean (segments + query order,
+    score + top-k, merge) ms per step, summed over this rank's shards."""
+    import numpy as np
+
+    for ix in indexes:
+        ix.set_option("timing", 1)
+    rows = []
+    for _ in range(max(3, min(steps, 10))):
+        ctx.flush.zero_()
+        step()
+        rows.append(tuple(map(sum, zip(*[ix.last_timing_ms() for ix in indexes]))))
+    for ix in indexes:
+        ix.set_option("timing", 0)
+    return np.array(rows).mean(axis=0)
+
+
+def roofline_record(ctx, posting_bytes, km, batch_bytes, ms_per_step):
+    score_ms = float(km[1])
+    achieved = posting_bytes / (score_ms * 1e-3) / 1e9
+    return {
+        "bound": "hbm", "kernel": "k_score_topk (score accumulation + per-range top-k)",
+        "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
+        "frac_of_nominal_8000": achieved / 8000.0, "peak_source": ctx.peak_src,
+        "algorithmic_bytes_per_launch": int(posting_bytes), "kernel_ms": score_ms,
+        "kernel_share_of_step": score_ms / float(km.sum()),
+        "other_kernels_ms": {"k_segments+k_query_order": float(km[0]), "k_merge": float(km[2])},
+        "whole_batch_GBps": batch_bytes / (ms_per_step * 1e-3) / 1e9,
+        # DRAM bytes per launch need a profiler; the ncu captures are committed under profiles/
+        # (r2_*_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum) -- nothing static is copied here
+        "traffic": None,
+    }
+
+
+def e2e_host(ctx, index, qn, k, steps, units):
+    """The call a user makes: bm25_search_host (pinned H2D of the queries + kernels + D2H of
+    ids and scores + synchronise) every step."""
+    import torch
+
+    for _ in range(2):
+        index.search(qn, k)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ctx.flush.zero_()
+        hid, hsc = index.search(qn, k)
+    torch.cuda.synchronize()
+    e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
+    return {"value": units / (e2e_s / steps), "unit": UNIT, "h2d_bytes_per_step": int(qn.nbytes),
+            "d2h_bytes_per_step": int(hid.nbytes + hsc.nbytes), "api": "bm25_search_host via DeviceIndex.search"}
+
+
+def measure_single(ctx, index, q, k, steps, warmup, want_e2e=True):
+    """One index on this rank, this rank's batch `q`: value / roofline / e2e of one workload."""
+    import torch
+
+    qn = q.cpu().numpy()
+    n_q = int(q.shape[0])
+    out_ids = torch.empty((n_q, k), dtype=torch.int32, device=ctx.dev)
+    out_sc = torch.empty((n_q, k), dtype=torch.float32, device=ctx.dev)
+
+    def step():
+        return index.search_device(q, k, out_ids=out_ids, out_scores=out_sc)
+
+    step_ms, ms_per_step, wall = timed_steps(ctx, step, steps, warmup)
+    km = kernel_split(ctx, [index], step, steps)
+    posting_bytes = index.posting_bytes(qn, 0)  # 8 * sum df (score kernel, SURVEY 8d)
+    units = n_q * ctx.world  # query-split: every rank answers its own batch
+    rec = {
+        "value": units / (ms_per_step / 1e3), "ms_per_step": ms_per_step, "steps": steps,
+        "roofline": roofline_record(ctx, posting_bytes, km, posting_bytes + 8 * k * n_q, ms_per_step),
+        "step_ms_min": float(min(step_ms)), "step_ms_median": float(sorted(step_ms)[len(step_ms) // 2]),
+        "wall_s_timed_region": wall,
+    }
+    if want_e2e:
+        rec["e2e"] = e2e_host(ctx, index, qn, k, steps, units)
+    return rec
+
+
+def sub_workload(ctx, name, k=0, steps=10, warmup=3, index=None, idx=None):
+    """A sub-record: another named workload (or another k on an existing index), same measurement."""
+    from mojo_bm25_b200 import engine, synth
+
+    args = ctx.args
+    own = index is None
+    if own:
+        idx, q, k0 = synth.make_workload(name, device=str(ctx.dev), index_seed=0, query_seed=1 + ctx.rank, scale=args.scale)
+        index = engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs)
+    else:
+        cfg = synth.WORKLOADS[name]
+        q = synth.synth_queries(idx.n_terms, cfg["n_queries"], cfg["n_query_terms"], r0=cfg.get("r0", 8),
+                                seed=1 + ctx.rank, device=str(ctx.dev), poisson_mean=cfg.get("poisson_mean"),
+                                max_terms=cfg.get("max_terms", 16), heavy_terms=cfg.get("heavy_terms", 0),
+                                heavy_range=cfg.get("heavy_range", 100))
+        k0 = min(cfg["k"], idx.n_docs)
+    k = k or k0
+    rec = measure_single(ctx, index, q, k, steps, warmup)
+    mode = "single" if ctx.world == 1 else "query-split"
+    rec["config"] = workload_config(args, name, idx.n_docs, idx.n_terms, idx.nnz, int(q.shape[0]), int(q.shape[1]), k,
+                                    synth.WORKLOADS[name].get("r0", 8), mode, ctx.world, 1)
+    rec["metric"], rec["unit"] = METRIC, UNIT
+    if own:
+        index.close()
+    return rec
+
+
+# ----------------------------------------------------------------------------------------------
+def run_doc_shard(ctx, workload, steps, warmup, scale=1.0, parity_queries=4, want_cpu=False):
+    """Config D (or --mode doc-shard on another workload): document-range shards, each its own
+    int32-indexed handle synthesised with seed = shard number; rank r owns shards r, r+W, ...
+    (strong scaling for D: a FIXED corpus of 8 shards x 12.5M docs and a fixed batch).  Every step:
+    local searches into the packed send buffer, one NCCL all-gather, the merge kernel."""
     import numpy as np
     import torch
 
     from mojo_bm25_b200 import engine, sharded, synth
 
-    rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl ours needs a CUDA device: the BM25 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=dev)
-    mode = args.mode
-    if mode == "auto":
-        mode = "query-split" if world > 1 and args.workload != "D" else ("doc-shard" if world > 1 else "single")
-    if args.workload == "D" and mode != "query-split":
-        mode = "doc-shard"  # the 100M-doc corpus only exists as 8 document shards, also on one GPU
-    elif world == 1:
-        mode = "single"
-
-    wl_cfg = synth.WORKLOADS[args.workload]
-    # doc-shard: the corpus is a set of document-range shards, each synthesised with seed = shard
-    #   number and searched through its own int32-indexed handle.  Workload D is a FIXED corpus of 8
-    #   shards x 12.5M docs = 100M docs (3e9 postings): rank r owns shards r, r+W, ... (strong scaling;
-    #   one GPU holds all 8).  Other workloads under --mode doc-shard get one shard per rank (weak).
-    # query-split / single: the same index (seed 0) on every rank, rank-specific queries (seed 1+rank).
-    if mode == "doc-shard":
-        total_shards = 8 if args.workload == "D" else world
-        if total_shards % world:
-            raise SystemExit(f"workload D has 8 document shards; --gpus must divide 8 (got {world})")
-        my_shards = list(range(rank, total_shards, world))
-    else:
-        total_shards, my_shards = 1, [0]
-    query_seed = 1 if mode == "doc-shard" else 1 + rank
+    world, rank, dev = ctx.world, ctx.rank, ctx.dev
+    total_shards = 8 if workload == "D" else world
+    if total_shards % world:
+        raise SystemExit(f"workload D has 8 document shards; --gpus must divide 8 (got {world})")
+    my_shards = list(range(rank, total_shards, world))
     indexes, synths, q, k = [], [], None, None
     for sh in my_shards:
-        idx, q, k = synth.make_workload(args.workload, device=str(dev), index_seed=sh, query_seed=query_seed,
-                                        scale=args.scale)
-        base = sh * idx.n_docs if mode == "doc-shard" else 0
-        ix = engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs, doc_id_base=base)
-        ix.set_option("timing", 1)
-        indexes.append(ix)
+        idx, q, k = synth.make_workload(workload, device=str(dev), index_seed=sh, query_seed=1, scale=scale)
+        indexes.append(engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs,
+                                                     doc_id_base=sh * idx.n_docs))
         synths.append(idx)
-    if args.k:
-        k = args.k
-    idx, index = synths[0], indexes[0]
+    if ctx.args.k:
+        k = ctx.args.k
+    n_q, n_docs = int(q.shape[0]), synths[0].n_docs
     qn = q.cpu().numpy()
-    n_q = q.shape[0]
-    posting_bytes = sum(ix.posting_bytes(qn, 0) for ix in indexes)  # 8 * sum df (score kernel)
-    batch_bytes = posting_bytes + 8 * k * n_q
-    out_ids = torch.empty((n_q, k), dtype=torch.int32, device=dev)
-    out_sc = torch.empty((n_q, k), dtype=torch.float32, device=dev)
-    searcher = sharded.DocShardedSearcher.from_index(indexes, k) if mode == "doc-shard" else None
+    searcher = sharded.DocShardedSearcher.from_index(indexes, k)
 
     def step():
-        if searcher is not None:
-            return searcher.search(q)
-        return index.search_device(q, k, out_ids=out_ids, out_scores=out_sc)
+        return searcher.search(q)
 
-    def kernel_ms():  # (segments, score, merge) device ms of this rank's last step, summed over its shards
-        return tuple(map(sum, zip(*[ix.last_timing_ms() for ix in indexes])))
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for _ in range(args.warmup):
-        flush.zero_()
+    step_ms, ms_per_step, wall = timed_steps(ctx, step, steps, warmup)
+    # second pass: where the step goes (device events; not inside the timed loop above)
+    searcher.timing = True
+    parts = []
+    for _ in range(max(3, min(steps, 5))):
+        ctx.flush.zero_()
         step()
-    torch.cuda.synchronize()
+        parts.append(searcher.last_timing_ms())
+    searcher.timing = False
+    local_ms, gather_ms, merge_ms = (ctx.max_over_ranks(float(x)) for x in np.array(parts).mean(axis=0))
+    km = kernel_split(ctx, indexes, step, steps)
+    posting_bytes = sum(ix.posting_bytes(qn, 0) for ix in indexes)
+    # e2e: pinned queries -> H2D -> local search(es) -> all-gather -> merge -> D2H of the result
+    q_pin = torch.from_numpy(qn).pin_memory()
+    q_dev = torch.empty_like(q)
+    for w in range(2 + steps):
+        if w == 2:
+            torch.cuda.synchronize()
+            ctx.barrier()
+            t0 = time.perf_counter()
+        ctx.flush.zero_()
+        q_dev.copy_(q_pin, non_blocking=True)
+        gi, gs = searcher.search(q_dev)
+        hid, hsc = gi.cpu(), gs.cpu()
+    e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
+    # parity: a query sample against the C oracle on the same shard arrays (outside any timed region)
+    from oracle import bm25_oracle as orc
+    from oracle import c_oracle
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = engine.kernel_launches()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    kern_ms = []
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.zero_()
-        starts[i].record()
-        step()
-        ends[i].record()
-        kern_ms.append(kernel_ms())  # waits for this step's kernels (device events)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    wall = time.perf_counter() - wall0
-    launches = engine.kernel_launches() - launches0
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = float(sum(step_ms))
-    if dist is not None:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    units = n_q * (world if mode == "query-split" else 1)  # queries the whole job answered per step
-    value = units / (ms_per_step / 1e3)
-
-    # ---- end-to-end through the host-buffer C-ABI call (pinned H2D + kernels + D2H each step) --
-    e2e = None
-    if mode != "doc-shard":
-        for _ in range(2):
-            index.search(qn, k)
-        if dist is not None:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            flush.zero_()
-            hid, hsc = index.search(qn, k)
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0)
-        if dist is not None:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e = {"value": units / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(qn.nbytes),
-               "d2h_bytes_per_step": int(hid.nbytes + hsc.nbytes), "api": "bm25_search_host via DeviceIndex.search"}
-    else:
-        # doc-shard e2e: pinned queries -> H2D -> local search(es) -> all-gather -> merge -> D2H of the result
-        q_pin = torch.from_numpy(qn).pin_memory()
-        q_dev = torch.empty_like(q)
-        for w in range(2 + args.steps):
-            if w == 2:
-                torch.cuda.synchronize()
-                if dist is not None:
-                    dist.barrier()
-                t0 = time.perf_counter()
-            flush.zero_()
-            q_dev.copy_(q_pin, non_blocking=True)
-            gi, gs = searcher.search(q_dev)
-            hid, hsc = gi.cpu(), gs.cpu()
-        e2e_s = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        e2e = {"value": units / (e2e_s / args.steps), "unit": UNIT, "h2d_bytes_per_step": int(qn.nbytes),
-               "d2h_bytes_per_step": int(hid.numel() * 4 + hsc.numel() * 4),
-               "api": "DocShardedSearcher.search (bm25_search per shard + all_gather + bm25_merge_topk)"}
-    clocks = sampler.stop()
-
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    peak, peak_src = load_peaks()
-    km = np.array(kern_ms)
-    score_ms = float(km[:, 1].mean())
-    achieved = posting_bytes / (score_ms * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": "k_score_topk (score accumulation + per-range top-k)",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "frac_of_nominal_8000": achieved / 8000.0, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": int(posting_bytes), "kernel_ms": score_ms,
-        "kernel_share_of_step": score_ms / float(km.sum(axis=1).mean()),
-        "other_kernels_ms": {"k_segments": float(km[:, 0].mean()), "k_merge": float(km[:, 2].mean())},
-        "whole_batch_GBps": batch_bytes / (ms_per_step * 1e-3) / 1e9,
-        "traffic": None,
-    }
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            tr = json.load(open(prof)).get(args.workload)
-            if tr:
-                roofline["traffic"] = tr["dram_bytes_per_launch"]
-                roofline["traffic_source"] = tr.get("source")
-        except Exception:  # noqa: BLE001
-            pass
-
+    sample = list(range(0, n_q, max(1, n_q // parity_queries)))[:parity_queries]
+    lists_i = np.zeros((len(my_shards), len(sample), k), np.int32)
+    lists_s = np.zeros((len(my_shards), len(sample), k), np.float32)
+    for s, (sh, idx) in enumerate(zip(my_shards, synths)):
+        indptr, indices, data = idx.numpy()
+        for j, qi in enumerate(sample):
+            dense = c_oracle.scores_dense(indptr, indices, data, idx.n_docs, qn[qi])
+            order = np.lexsort((np.arange(idx.n_docs), -dense.astype(np.float64)))[:k]
+            lists_i[s, j], lists_s[s, j] = order + sh * idx.n_docs, dense[order]
+        del indptr, indices, data
+    if ctx.dist is not None:
+        gathered = [None] * world
+        ctx.dist.all_gather_object(gathered, (lists_i, lists_s))
+        lists_i = np.concatenate([g[0] for g in gathered])
+        lists_s = np.concatenate([g[1] for g in gathered])
+    want_i, want_s = orc.merge_topk_lists(lists_i, lists_s, k)
+    got_i, got_s = hid.numpy()[sample], hsc.numpy()[sample]
+    parity_ok = bool(np.array_equal(got_i, want_i) and np.array_equal(got_s.view(np.uint32), want_s.view(np.uint32)))
+    if not parity_ok:
+        raise SystemExit("doc-shard parity check against the oracle FAILED")
     cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    if want_cpu and rank == 0:
         from oracle import cpu_baseline
 
         cores = cpu_baseline.host_cores()
-        n_sample = cpu_sample_size(n_q, idx.n_docs, cores, args.cpu_sample)
-        indptr, indices, data = idx.numpy()
-        res = run_cpu_port(indptr, indices, data, idx.n_docs, qn[:n_sample], k, 1, 0)
+        n_sample = cpu_sample_size(n_q, n_docs, cores, ctx.args.cpu_sample)
+        indptr, indices, data = synths[0].numpy()
+        res = run_cpu_port(indptr, indices, data, n_docs, qn[:n_sample], k, 1, 0)
         cpu = {"value": res["qps"] / total_shards, "unit": UNIT, "cores": res["cores"], "kind": "port",
-               "sample": f"first {n_sample} of {n_q} queries of the same batch, oracle port of BM25v.search, "
-                         f"{res['cores']} forked workers, {res['step_seconds'][0]:.2f} s"
-                         + (f"; timed on shard 0 of {total_shards} and divided by {total_shards} (a query visits every shard)"
-                            if total_shards > 1 else "")}
-
-    par = {"single": "1 GPU", "query-split": f"query-split x{world}: index replicated, each rank answers its own "
-           f"{n_q}-query batch, no data-path collective",
-           "doc-shard": f"doc-shard x{world}: {total_shards} shards of {idx.n_docs} docs ({idx.n_docs * total_shards} "
-           f"total), {len(my_shards)} per rank, same batch on every rank, local top-k + NCCL all-gather of "
-           f"{n_q * k * 8 * len(my_shards)} B per rank + merge kernel"}[mode]
-    strong = mode == "doc-shard" and args.workload == "D"
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
-        "vs_baseline": None, "dtype": DTYPE,
-        "data": "synthetic", "config": workload_config(args, wl_cfg, idx, q, k, {"parallelism": par, "shards": total_shards}),
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "wall_s_timed_region": wall, "step_ms_min": float(min(step_ms)), "step_ms_median": float(np.median(step_ms)),
+               "sample": f"first {n_sample} of {n_q} queries, oracle port of BM25v.search, {res['cores']} forked workers, "
+                         f"{res['step_seconds'][0]:.2f} s; timed on shard 0 of {total_shards} and divided by "
+                         f"{total_shards} (a query visits every shard)"}
+    rec = {
+        "metric": METRIC, "unit": UNIT, "value": n_q / (ms_per_step / 1e3), "ms_per_step": ms_per_step, "steps": steps,
+        "scaling": "strong" if workload == "D" else "weak", "n_gpus": world,
+        "local_ms": local_ms, "all_gather_ms": gather_ms, "merge_ms": merge_ms,
+        "all_gather_bytes_per_rank": int(n_q * k * 8 * len(my_shards)),
+        "parity_checked": len(sample), "parity": "bit-exact vs C oracle (ids and score bits)",
+        "e2e": {"value": n_q / (e2e_s / steps), "unit": UNIT, "h2d_bytes_per_step": int(qn.nbytes),
+                "d2h_bytes_per_step": int(hid.numel() * 4 + hsc.numel() * 4),
+                "api": "DocShardedSearcher.search (bm25_search per shard + all_gather + bm25_merge_topk)"},
+        "roofline": roofline_record(ctx, posting_bytes, km, posting_bytes + 8 * k * n_q, ms_per_step),
+        "config": workload_config(ctx.args, workload, n_docs, synths[0].n_terms, synths[0].nnz, n_q, int(q.shape[1]), k,
+                                  synth.WORKLOADS[workload].get("r0", 8), "doc-shard", world, total_shards),
+        "step_ms_min": float(min(step_ms)), "wall_s_timed_region": wall,
     }
-    print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    if cpu:
+        rec["cpu_baseline"] = cpu
+    for ix in indexes:
+        ix.close()
+    del indexes, synths, searcher
+    torch.cuda.empty_cache()
+    return rec
+
+
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+
+    from mojo_bm25_b200 import engine, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: the BM25 path has no CPU fallback")
+    ctx = Ctx(args)
+    rank, world = ctx.rank, ctx.world
+    mode = headline_mode(args, world)
+    sampler = ClockSampler(ctx.local)
+    sampler.start()
+    launches0 = engine.kernel_launches()
+    wl_cfg = synth.WORKLOADS[args.workload]
+    subs = {}
+
+    if mode == "doc-shard":
+        rec = run_doc_shard(ctx, args.workload, args.steps, args.warmup, scale=args.scale,
+                            want_cpu=not args.no_cpu_baseline and world == 1)
+        launches = engine.kernel_launches() - launches0
+        line = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
+                "scaling": rec["scaling"], "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+                "config": rec["config"], "e2e": rec["e2e"], "gpu_launches": int(launches), "roofline": rec["roofline"],
+                "cpu_baseline": rec.get("cpu_baseline"), "doc_shard": rec}
+    else:
+        # headline: the same index (seed 0) on every rank, rank-specific queries (seed 1 + rank)
+        idx, q, k = synth.make_workload(args.workload, device=str(ctx.dev), index_seed=0, query_seed=1 + rank,
+                                        scale=args.scale)
+        if args.k:
+            k = args.k
+        index = engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs)
+        rec = measure_single(ctx, index, q, k, args.steps, args.warmup)
+        launches = engine.kernel_launches() - launches0  # headline only: timed loop + kernel-split pass + e2e
+        n_q = int(q.shape[0])
+        shape = (idx.n_docs, idx.n_terms, idx.nnz)
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import cpu_baseline
+
+            cores = cpu_baseline.host_cores()
+            n_sample = cpu_sample_size(n_q, idx.n_docs, cores, args.cpu_sample)
+            indptr, indices, data = idx.numpy()
+            res = run_cpu_port(indptr, indices, data, idx.n_docs, q.cpu().numpy()[:n_sample], k, 1, 0)
+            cpu = {"value": res["qps"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                   "sample": f"first {n_sample} of {n_q} queries of the same batch, oracle port of BM25v.search, "
+                             f"{res['cores']} forked workers, {res['step_seconds'][0]:.2f} s"}
+        if not args.no_subrecords and args.scale == 1.0:
+            sub_steps = max(5, min(args.steps, 10))
+            if args.workload == "B":
+                subs["k100"] = sub_workload(ctx, "B", k=100, steps=sub_steps, index=index, idx=idx)
+                subs["wE"] = sub_workload(ctx, "E", steps=sub_steps, index=index, idx=idx)  # E queries, same 1M-doc index
+        index.close()
+        del index, idx
+        torch.cuda.empty_cache()
+        if not args.no_subrecords and args.scale == 1.0:
+            sub_steps = max(5, min(args.steps, 10))
+            if args.workload != "10M":
+                subs["w10M"] = sub_workload(ctx, "10M", steps=sub_steps)
+            torch.cuda.empty_cache()
+            if world == 1 and args.workload != "C":
+                subs["wC"] = sub_workload(ctx, "C", steps=5)
+            torch.cuda.empty_cache()
+            if 8 % world == 0:
+                subs["doc_shard"] = run_doc_shard(ctx, "D", max(3, min(args.steps, 5)), 3, scale=args.doc_shard_scale)
+        line = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+                "config": workload_config(args, args.workload, shape[0], shape[1], shape[2], n_q, int(q.shape[1]), k,
+                                          wl_cfg.get("r0", 8), mode, world, 1),
+                "e2e": rec["e2e"], "gpu_launches": int(launches), "roofline": rec["roofline"], "cpu_baseline": cpu,
+                "wall_s_timed_region": rec["wall_s_timed_region"], "step_ms_min": rec["step_ms_min"],
+                "step_ms_median": rec["step_ms_median"]}
+        line.update(subs)
+    line["clocks"] = sampler.stop()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if ctx.dist is not None:
+        ctx.dist.barrier()
+        ctx.dist.destroy_process_group()
 
 
 def main():

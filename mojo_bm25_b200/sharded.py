@@ -56,6 +56,8 @@ class DocShardedSearcher:
         self.merge = merge
         self._send = None
         self._recv = None
+        self.timing = False  # record CUDA events around local searches / all-gather / merge
+        self._ev = None
 
     @classmethod
     def from_index(cls, index, k: int, group=None):
@@ -80,6 +82,12 @@ class DocShardedSearcher:
         n_queries = queries.shape[0]
         n_local = len(self.local_searches)
         send, recv = self._buffers(n_queries, queries.device)
+        ev = None
+        if self.timing and queries.is_cuda:
+            if self._ev is None:
+                self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev = self._ev
+            ev[0].record()
         for s, local in enumerate(self.local_searches):
             k_local = self.k if self.shard_docs is None else min(self.k, self.shard_docs[s])
             if k_local == self.k:
@@ -93,14 +101,28 @@ class DocShardedSearcher:
                 local(queries, k_local, ids, sc)
                 send[s, 0, :, :k_local].copy_(ids)
                 send[s, 1, :, :k_local].view(torch.float32).copy_(sc)
+        if ev:
+            ev[1].record()
         if self.world > 1:
             dist.all_gather_into_tensor(recv.view(self.world * n_local * 2, n_queries, self.k),
                                         send.view(n_local * 2, n_queries, self.k), group=self.group)
         else:
             recv[0].copy_(send)
-        return self.merge(recv[0, 0, 0], recv[0, 0, 1].view(torch.float32), self.k,
-                          list_stride=2 * n_queries * self.k, n_lists=self.world * n_local,
-                          n_queries=n_queries, k_in=self.k)
+        if ev:
+            ev[2].record()
+        out = self.merge(recv[0, 0, 0], recv[0, 0, 1].view(torch.float32), self.k,
+                         list_stride=2 * n_queries * self.k, n_lists=self.world * n_local,
+                         n_queries=n_queries, k_in=self.k)
+        if ev:
+            ev[3].record()
+        return out
+
+    def last_timing_ms(self):
+        """(local searches, all-gather [device copy at world 1], merge) device ms of the last search
+        (needs ``timing = True``); waits for that search."""
+        ev = self._ev
+        ev[3].synchronize()
+        return ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
 
 
 class QuerySplitSearcher:
