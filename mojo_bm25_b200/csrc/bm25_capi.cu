@@ -166,7 +166,7 @@ struct bm25_index {
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
     int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_heavy_min = 0, opt_cand_smem = 0;
-    int opt_poison = 0, opt_no_bulk_clear = 0, opt_no_query_sort = 0;
+    int opt_poison = 0, opt_no_bulk_clear = 0, opt_no_query_sort = 0, opt_generic_kernel = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace: one per handle; searches on different streams are ordered through ws_done
@@ -220,7 +220,7 @@ int finish_create(bm25_index* ix, const cudaDeviceProp& prop, const int32_t* d_i
     for (int64_t t = 0; t < V; ++t) {
         const int64_t df = ix->h_indptr[t + 1] - ix->h_indptr[t];
         tptr[t] = make_int2((int)pos, (int)(pos + df));
-        pos += (df + 3) & ~(int64_t)3;
+        pos += (df + 4) & ~(int64_t)3;  // >= 1 sentinel posting after every list, starts 16-byte aligned
         if (pos > 0x7fffffffLL - 8)
             return fail(BM25_ERR_UNSUPPORTED, "index too large for int32 posting offsets after padding (%lld)",
                         (long long)pos);
@@ -472,7 +472,16 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
         k_scores_dense<<<(unsigned)grid, kThreads, lp.smem, st>>>(a);
     } else {
         static thread_local size_t configured[2][64] = {{0}, {0}};
-        if (lp.warps <= BM25_LB_T / 32) {
+        static thread_local size_t configured_s[2][64] = {{0}, {0}};
+        if (a.T <= 32 && !ix->opt_generic_kernel) {  // lane-per-term specialisation
+            if (lp.warps <= BM25_LB_T / 32) {
+                if ((rc = configure_smem(k_score_topk_s<BM25_LB_T>, lp.smem, ix->smem_optin, &configured_s[0][ix->device % 64]))) return rc;
+                k_score_topk_s<BM25_LB_T><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
+            } else {
+                if ((rc = configure_smem(k_score_topk_s<512>, lp.smem, ix->smem_optin, &configured_s[1][ix->device % 64]))) return rc;
+                k_score_topk_s<512><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
+            }
+        } else if (lp.warps <= BM25_LB_T / 32) {
             if ((rc = configure_smem(k_score_topk<BM25_LB_T>, lp.smem, ix->smem_optin, &configured[0][ix->device % 64]))) return rc;
             k_score_topk<BM25_LB_T><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
         } else {
@@ -844,6 +853,8 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
     } else if (!strcmp(name, "heavy_min")) {
         if (value < 0 || value > (1 << 28)) return fail(BM25_ERR_INVALID, "heavy_min out of range");
         ix->opt_heavy_min = (int)value;
+    } else if (!strcmp(name, "generic_kernel")) {
+        ix->opt_generic_kernel = value ? 1 : 0;
     } else if (!strcmp(name, "no_query_sort")) {
         ix->opt_no_query_sort = value ? 1 : 0;
     } else if (!strcmp(name, "no_bulk_clear")) {

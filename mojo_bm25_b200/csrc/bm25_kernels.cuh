@@ -65,8 +65,9 @@ constexpr int kStateInts = 8;         // ints of cursor state per (warp, query t
 // ---------------------------------------------------------------------------------------------
 // The index in HBM ("re-bucketed into document-range tiles", built at load time):
 //   ids / w     posting arrays in the PADDED layout: every term's posting list starts at a multiple
-//               of 4 elements (16 bytes) and is padded at the end with (kDocNone, 0.0) postings up
-//               to the next multiple of 4, so that 16-byte vector loads never straddle two terms.
+//               of 4 elements (16 bytes) and is followed by 1..4 sentinel postings (kDocNone, 0.0)
+//               up to the next multiple of 4, so that 16-byte vector loads never straddle two
+//               terms and a cursor that runs off a list reads a sentinel instead of needing an end.
 //   tptr[t]     {start, end} of term t's list in the padded arrays (end - start = df_t).
 //   term_row[t] row of term t in the tile table, or -1.  "Heavy" terms (df_t >= heavy_min postings
 //               per document tile on average) own a row; "light" terms are walked with cursors.
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(128) k_relayout(const int32_t* __restrict__ in
         const int s = indptr[t];
         const int n = indptr[t + 1] - s;
         const int o = tptr[t].x;
-        const int padded = (n + 3) & ~3;
+        const int padded = (n + 4) & ~3;  // >= 1 sentinel after the last posting
         for (int i = threadIdx.x; i < padded; i += blockDim.x) {
             ids_out[o + i] = i < n ? ids_in[s + i] : kDocNone;
             w_out[o + i] = i < n ? w_in[s + i] : 0.f;
@@ -1010,6 +1011,373 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
                 }
                 __syncwarp();
                 if (lm) light_visits(lm, g0);
+            }
+            // ---- end of tile: the common case is a write-only clear ---------------------------
+            const bool cold = a.general || (touched && hl_n != 0) || ld_volatile(&sh.overflow);
+            if (!cold) {
+                if (touched) {
+                    if (a.bulk_clear) {
+                        smem_bulk_zero(tile, uS * 4u);
+                    } else {
+                        for (unsigned off = lane * 16u; off < uS * 4u; off += 512u) sts_zero16(tile + off);
+                    }
+                }
+            } else {
+                theta_f = tile_finish(cold_ctx(), base, min(S, a.n_docs - base), hl_n,
+                                      (hl_n <= kHotCap && !a.general) ? 1 : 0);
+            }
+        }
+        cp_async_wait_all();  // nothing of this warp may still be in flight towards shared memory
+    }
+    cta_finish(cold_ctx(), a.cand_global != nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_score_topk_s: the same kernel specialised for queries of at most 32 term slots (every
+// BASELINE config except the 64-term stress).  Lane t owns query term t for the whole chunk:
+//   * its class (heavy / light / none), its tile-table row pointer or its cursor live in registers;
+//   * its 16 bytes of shared state are {ring of 4 table entries} (heavy) or {doc0, w0, doc1, w1},
+//     the two resident postings of the cursor (light) -- cp.async targets, one LDS per tile;
+//   * heavy terms with at most 32 postings in the tile are fetched as NARROW pieces (one posting
+//     per lane, 4-byte loads, one read-modify-write) instead of 128-posting pieces;
+//   * a light term's postings are added by its own lane; posting lists are sentinel-terminated
+//     (>= 1 kDocNone after the last posting), so a cursor needs no end pointer.
+// shared memory: same carve-up as k_score_topk (state area: 16 bytes per term are used).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lds_v2(unsigned a, int& x, int& y) {
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_v2(unsigned a, int x, int y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
+struct PieceRegs {
+    int4 d;
+    float4 w;
+    // 128 postings from p0 (multiple of 4), four per lane
+    __device__ __forceinline__ void load_wide(const int32_t* __restrict__ ids, const float* __restrict__ wts, int p0, int hi,
+                                              int lane) {
+        const int idx = p0 + 4 * lane;
+        d = make_int4(kDocNone, kDocNone, kDocNone, kDocNone);
+        w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < hi) {
+            d = __ldg(reinterpret_cast<const int4*>(ids + idx));
+            w = __ldg(reinterpret_cast<const float4*>(wts + idx));
+        }
+    }
+    // up to 32 postings [lo, hi), one per lane (component x)
+    __device__ __forceinline__ void load_narrow(const int32_t* __restrict__ ids, const float* __restrict__ wts, int lo, int hi,
+                                                int lane) {
+        const int idx = lo + lane;
+        d.x = kDocNone;
+        w.x = 0.f;
+        if (idx < hi) {
+            d.x = __ldg(ids + idx);
+            w.x = __ldg(wts + idx);
+        }
+    }
+    __device__ __forceinline__ void add_wide(unsigned tile, int base, unsigned S, float& n0, float& n1, float& n2,
+                                             float& n3) const {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p0, p1, p2, p3;\n\t"
+            ".reg .u32 s0, s1, s2, s3;\n\t"
+            ".reg .f32 v0, v1, v2, v3;\n\t"
+            "sub.u32 s0, %4, %12;\n\t"
+            "sub.u32 s1, %5, %12;\n\t"
+            "sub.u32 s2, %6, %12;\n\t"
+            "sub.u32 s3, %7, %12;\n\t"
+            "setp.lt.u32 p0, s0, %13;\n\t"
+            "setp.lt.u32 p1, s1, %13;\n\t"
+            "setp.lt.u32 p2, s2, %13;\n\t"
+            "setp.lt.u32 p3, s3, %13;\n\t"
+            "mad.lo.u32 s0, s0, 4, %14;\n\t"
+            "mad.lo.u32 s1, s1, 4, %14;\n\t"
+            "mad.lo.u32 s2, s2, 4, %14;\n\t"
+            "mad.lo.u32 s3, s3, 4, %14;\n\t"
+            "mov.f32 %0, 0f00000000;\n\t"
+            "mov.f32 %1, 0f00000000;\n\t"
+            "mov.f32 %2, 0f00000000;\n\t"
+            "mov.f32 %3, 0f00000000;\n\t"
+            "@p0 ld.shared.f32 v0, [s0];\n\t"
+            "@p1 ld.shared.f32 v1, [s1];\n\t"
+            "@p2 ld.shared.f32 v2, [s2];\n\t"
+            "@p3 ld.shared.f32 v3, [s3];\n\t"
+            "@p0 add.f32 %0, v0, %8;\n\t"
+            "@p1 add.f32 %1, v1, %9;\n\t"
+            "@p2 add.f32 %2, v2, %10;\n\t"
+            "@p3 add.f32 %3, v3, %11;\n\t"
+            "@p0 st.shared.f32 [s0], %0;\n\t"
+            "@p1 st.shared.f32 [s1], %1;\n\t"
+            "@p2 st.shared.f32 [s2], %2;\n\t"
+            "@p3 st.shared.f32 [s3], %3;\n\t"
+            "}"
+            : "=&f"(n0), "=&f"(n1), "=&f"(n2), "=&f"(n3)
+            : "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w), "r"(base), "r"(S),
+              "r"(tile)
+            : "memory");
+    }
+    __device__ __forceinline__ float add_narrow(unsigned tile, int base, unsigned S) const {
+        float n0;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p0;\n\t"
+            ".reg .u32 s0;\n\t"
+            ".reg .f32 v0;\n\t"
+            "sub.u32 s0, %1, %3;\n\t"
+            "setp.lt.u32 p0, s0, %4;\n\t"
+            "mad.lo.u32 s0, s0, 4, %5;\n\t"
+            "mov.f32 %0, 0f00000000;\n\t"
+            "@p0 ld.shared.f32 v0, [s0];\n\t"
+            "@p0 add.f32 %0, v0, %2;\n\t"
+            "@p0 st.shared.f32 [s0], %0;\n\t"
+            "}"
+            : "=&f"(n0)
+            : "r"(d.x), "f"(w.x), "r"(base), "r"(S), "r"(tile)
+            : "memory");
+        return n0;
+    }
+};
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_score_topk_s(const SearchArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int NCW = blockDim.x >> 5;
+    const int T = a.T, S = a.tile_docs;
+    float* sc = reinterpret_cast<float*>(smem_raw);
+    u64* cand_smem = reinterpret_cast<u64*>(sc + (size_t)NCW * S);
+    int* st_all = reinterpret_cast<int*>(cand_smem + (a.cand_global ? 0 : a.cap));
+    unsigned short* st_hot = reinterpret_cast<unsigned short*>(st_all + (size_t)NCW * kStateInts * T);
+    __shared__ CtaShared sh;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int qslot = blockIdx.x / a.splits;
+    const int sp = blockIdx.x - qslot * a.splits;
+    const int q = a.qperm ? __ldg(a.qperm + qslot) : qslot;
+    const int chunk = sp * NCW + warp;
+
+    if (a.poison) {  // debug: no read of uninitialised shared memory may go unnoticed
+        unsigned* all = reinterpret_cast<unsigned*>(smem_raw);
+        const size_t words = ((size_t)NCW * S * 4 + (a.cand_global ? 0 : (size_t)a.cap * 8) +
+                              (size_t)NCW * kStateInts * T * 4 + (size_t)NCW * kHotCap * 2) / 4;
+        for (size_t i = tid; i < words; i += blockDim.x) all[i] = 0xffffffffu;
+        __syncthreads();
+    }
+    float* scw = sc + (size_t)warp * S;
+    for (int i = lane * 4; i < S; i += 128) *reinterpret_cast<float4*>(scw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) {
+        sh.ncand = 0;
+        sh.overflow = 0;
+        const u64 shared_theta = a.theta_q ? *reinterpret_cast<volatile u64*>(a.theta_q + q) : 0ull;
+        sh.theta = shared_theta > a.theta0 ? shared_theta : a.theta0;
+    }
+    __syncthreads();
+
+    auto cold_ctx = [&]() {
+        ColdCtx c;
+        c.cand = a.cand_global ? a.cand_global + ((size_t)q * a.splits + sp) * a.cap : cand_smem;
+        c.out = a.partial + ((int64_t)q * a.splits + sp) * a.k;
+        c.theta_q = a.theta_q ? a.theta_q + q : nullptr;
+        c.theta0 = a.theta0;
+        c.sh = &sh;
+        c.scw = scw;
+        c.hot = st_hot + warp * kHotCap;
+        c.cap = a.cap;
+        c.k = a.k;
+        c.S = S;
+        c.general = a.general;
+        c.nthreads = (int)blockDim.x;
+        c.tid = tid;
+        return c;
+    };
+
+    if (chunk < a.n_chunks) {
+        const unsigned st = smem_u32(st_all + (size_t)warp * kStateInts * T) + 16u * lane;  // this lane's 16 bytes
+        const unsigned tile = smem_u32(scw);
+        const unsigned hot_s = smem_u32(st_hot + warp * kHotCap);
+        const unsigned uS = (unsigned)S;
+        const int NB = a.n_tiles;
+        const int j0 = chunk * a.tiles_per_chunk;
+        const int j1 = min(NB, j0 + a.tiles_per_chunk);
+        const bool hot_enabled = !a.general && !a.no_hot;
+        float theta_f;
+        {
+            const u64 t0 = sh.theta;
+            theta_f = (t0 == 0ull) ? -INFINITY : (a.general ? key_score(t0) : fmaxf(key_score(t0), 1.401298464e-45f));
+        }
+        // ---- this lane's term -------------------------------------------------------------------
+        const int32_t* tabp = nullptr;  // heavy: row of the tile table
+        int hi_prev = 0;                // heavy: table entry of the current tile (= end of the previous one)
+        int lpos = -1;                  // light: posting index of the first resident posting (-1: no term)
+        if (lane < T) {
+            const int term = __ldg(a.queries + (int64_t)q * T + lane);
+            if (term >= 0 && term < a.n_terms) {
+                const int row = __ldg(a.term_row + term);
+                if (row >= 0) {
+                    tabp = a.tab + (int64_t)row * (NB + 1);
+                    hi_prev = __ldg(tabp + j0);
+                    sts_i32(st + 4u * ((j0 + 1) & 3), __ldg(tabp + min(j0 + 1, NB)));
+                    sts_i32(st + 4u * ((j0 + 2) & 3), __ldg(tabp + min(j0 + 2, NB)));
+                } else {
+                    lpos = __ldg(a.seg + ((int64_t)q * (a.n_chunks + 1) + chunk) * T + lane);
+                    sts_i32(st + 0, __ldg(a.ids + lpos));
+                    sts_i32(st + 4, __float_as_int(__ldg(a.w + lpos)));
+                    sts_i32(st + 8, __ldg(a.ids + lpos + 1));
+                    sts_i32(st + 12, __float_as_int(__ldg(a.w + lpos + 1)));
+                }
+            }
+        }
+        const bool heavy = tabp != nullptr;
+        const bool light = lpos >= 0;
+        const unsigned st0 = st - 16u * lane;  // state of term 0 (warp-uniform)
+
+        for (int j = j0; j < j1; ++j) {
+            cp_async_wait_all();  // table entries / cursor refills requested during the previous tiles
+            __syncwarp();
+            const int base = j * S;
+            const int tile_end = base + S;
+            bool refill_inflight = false;  // a light-term refill was requested during THIS tile
+            int hl_n = hot_enabled ? 0 : kHotCap + 1;  // hot-list length; > kHotCap: overflowed / disabled
+            int lo = 0, hi = 0, hd = kDocNone;
+            if (heavy) {
+                lo = hi_prev;
+                hi = lds_i32(st + 4u * ((j + 1) & 3));
+                cp_async4_s(st + 4u * ((j + 3) & 3), tabp + min(j + 3, NB));
+                hi_prev = hi;
+            } else if (light) {
+                hd = lds_i32(st);
+            }
+            unsigned hm = __ballot_sync(kFull, hi > lo);        // heavy terms with postings in this tile
+            unsigned lm = __ballot_sync(kFull, hd < tile_end);  // light terms with postings in this tile
+            const bool touched = (hm | lm) != 0u;
+
+            // warp-collective: append the tile slots of the lanes with `hot` to the hot list
+            auto hot_add = [&](bool hot, int slot) {
+                const unsigned m = __ballot_sync(kFull, hot);
+                if (m == 0u) return;
+                const int c = __popc(m);
+                if (hl_n + c <= kHotCap) {
+                    unsigned lt;
+                    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+                    if (hot) asm volatile("st.shared.u16 [%0], %1;" ::"r"(hot_s + 2u * (hl_n + __popc(m & lt))), "h"((unsigned short)slot) : "memory");
+                    hl_n += c;
+                } else {
+                    hl_n = kHotCap + 1;
+                }
+            };
+
+            // light terms of `mask` (bit = lane = term), in query order; the owner lane adds its
+            // cursor's resident postings and moves the cursor
+            auto light_visits = [&](unsigned mask) {
+                while (mask) {
+                    const int tl = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const unsigned s = st0 + 16u * tl;
+                    for (;;) {
+                        int d0, w0;
+                        lds_v2(s, d0, w0);
+                        if (d0 >= tile_end) break;
+                        bool hot = false;
+                        if (lane == tl) {
+                            const unsigned slot = tile + 4u * (unsigned)(d0 - base);
+                            const float nw = lds_f32(slot) + __int_as_float(w0);
+                            sts_f32(slot, nw);
+                            hot = nw >= theta_f;
+                        }
+                        if (hl_n <= kHotCap) hot_add(hot, d0 - base);
+                        if (refill_inflight) {  // the second resident posting may still be on its way
+                            cp_async_wait_all();
+                            refill_inflight = false;
+                        }
+                        __syncwarp();
+                        if (lane == tl) {
+                            int d1, w1;
+                            lds_v2(s + 8, d1, w1);
+                            sts_v2(s, d1, w1);
+                            lpos += 1;
+                            cp_async4_s(s + 8, a.ids + lpos + 1);
+                            cp_async4_s(s + 12, a.w + lpos + 1);
+                        }
+                        refill_inflight = true;
+                        __syncwarp();
+                    }
+                }
+            };
+
+            if (touched) {
+                // ---- accumulate: terms strictly in query order --------------------------------
+                // piece generator over the heavy terms (warp-uniform state)
+                int gp = 0, ghi = 0, gt = 0;
+                auto next_piece = [&](bool& first, bool& narrow) -> bool {
+                    if (gp + 128 < ghi) {  // only reached for wide terms
+                        gp += 128;
+                        first = false;
+                        narrow = false;
+                        return true;
+                    }
+                    if (hm == 0u) return false;
+                    gt = __ffs(hm) - 1;
+                    hm &= hm - 1;
+                    const int glo = __shfl_sync(kFull, lo, gt);
+                    ghi = __shfl_sync(kFull, hi, gt);
+                    narrow = ghi - glo <= 32;
+                    gp = narrow ? glo : (glo & ~3);
+                    first = true;
+                    return true;
+                };
+                auto fetch = [&](PieceRegs& P, bool narrow) {
+                    if (narrow) P.load_narrow(a.ids, a.w, gp, ghi, lane);
+                    else P.load_wide(a.ids, a.w, gp, ghi, lane);
+                };
+                auto consume = [&](const PieceRegs& P, bool first, bool narrow, int tt) {
+                    if (first) {  // a new term: first the light terms that precede it in the query
+                        const unsigned pl = lm & ((1u << tt) - 1u);
+                        if (pl) {
+                            __syncwarp();
+                            lm &= ~pl;
+                            light_visits(pl);
+                        }
+                        __syncwarp();
+                    }
+                    if (narrow) {
+                        const float n0 = P.add_narrow(tile, base, uS);
+                        if (hl_n <= kHotCap) hot_add(n0 >= theta_f, P.d.x - base);  // outside the tile: n0 = 0 < theta_f
+                    } else {
+                        float n0, n1, n2, n3;
+                        P.add_wide(tile, base, uS, n0, n1, n2, n3);
+                        if (hl_n <= kHotCap) {
+                            if (__any_sync(kFull, fmaxf(fmaxf(n0, n1), fmaxf(n2, n3)) >= theta_f)) {
+                                hot_add(n0 >= theta_f, P.d.x - base);
+                                hot_add(n1 >= theta_f, P.d.y - base);
+                                hot_add(n2 >= theta_f, P.d.z - base);
+                                hot_add(n3 >= theta_f, P.d.w - base);
+                            }
+                        }
+                    }
+                };
+                // ping-pong: the piece after the current one is requested before the current one is added
+                PieceRegs A, B;
+                A.d = B.d = make_int4(kDocNone, kDocNone, kDocNone, kDocNone);
+                A.w = B.w = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool fA = false, fB = false, nA = false, nB = false;
+                bool more = next_piece(fA, nA);
+                int tA = gt, tB = 0;
+                if (more) fetch(A, nA);
+                while (more) {
+                    more = next_piece(fB, nB);
+                    tB = gt;
+                    if (more) fetch(B, nB);
+                    consume(A, fA, nA, tA);
+                    if (!more) break;
+                    more = next_piece(fA, nA);
+                    tA = gt;
+                    if (more) fetch(A, nA);
+                    consume(B, fB, nB, tB);
+                }
+                __syncwarp();
+                if (lm) light_visits(lm);
             }
             // ---- end of tile: the common case is a write-only clear ---------------------------
             const bool cold = a.general || (touched && hl_n != 0) || ld_volatile(&sh.overflow);

@@ -11,7 +11,7 @@ from oracle import c_oracle
 
 pytestmark = pytest.mark.gpu
 
-NAMES = ["cap", "consumer_warps", "tile_docs", "cand_smem", "poison", "splits", "heavy_min", "no_hot"]
+NAMES = ["cap", "consumer_warps", "tile_docs", "cand_smem", "poison", "splits", "heavy_min", "no_hot", "generic_kernel"]
 
 
 def _variants(k):
@@ -23,6 +23,7 @@ def _variants(k):
     out.append(dict(cap=k + 64, consumer_warps=8, tile_docs=2048, poison=1, splits=1))
     out.append(dict(cap=k + 64, consumer_warps=4, tile_docs=512, poison=1, heavy_min=1 << 20))
     out.append(dict(cap=k + 64, consumer_warps=4, tile_docs=512, poison=1, no_hot=1))
+    out.append(dict(cap=k + 64, consumer_warps=4, tile_docs=512, poison=1, generic_kernel=1))
     return out
 
 
