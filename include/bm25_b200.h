@@ -85,8 +85,8 @@ int bm25_index_get_info(const bm25_index* index, bm25_index_info* out);
  *   "cap"            candidate-buffer keys per CTA (default max(4k, 512) up to k = 1024, else 2k; power of two)
  *   "force_general"  1: treat the index as if it held non-positive weights (every doc competes)
  *   "cand_smem"      1: keep the candidate buffer in shared memory also for k > 256
- *   "heavy_min"      a term gets a row in the tile table when df*16 >= heavy_min * n_tiles (default 32,
- *                    i.e. two postings per document tile on average); lighter terms are walked by cursors
+ *   "heavy_min"      a term gets a row in the tile table when df*16 >= heavy_min * n_tiles (default 16,
+ *                    i.e. one posting per document tile on average); lighter terms are walked by cursors
  *   "poison"         1 (debug): fill workspace and shared memory with 0xff before every search
  *   "no_hot" / "no_priming" / "no_theta_share"   1: disable the hot-list epilogue / the load-time
  *                    threshold priming / the per-query threshold shared between CTAs (A/B switches)

@@ -258,7 +258,7 @@ int finish_create(bm25_index* ix, const cudaDeviceProp& prop, const int32_t* d_i
 // size or the heavy-term threshold changes).  heavy_min is in 1/16 postings per tile: a term is
 // heavy when df * 16 >= heavy_min * n_tiles.
 int ensure_table(bm25_index* ix, int S) {
-    int hm = ix->opt_heavy_min > 0 ? ix->opt_heavy_min : 32;
+    int hm = ix->opt_heavy_min > 0 ? ix->opt_heavy_min : 16;
     if (ix->tab_tile_docs == S && ix->tab_heavy_min == hm) return BM25_OK;
     CU(cudaDeviceSynchronize());  // no search may still be reading the old table
     const int64_t V = ix->n_terms;
@@ -439,6 +439,9 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
         const int64_t waves = ix->opt_waves > 0 ? ix->opt_waves : (k > 256 ? 4 : 10);
         const int64_t want = waves * per_sm * ix->sm_count;  // CTAs in flight x waves
         splits = (int)std::max<int64_t>(1, (want + Q - 1) / std::max<int64_t>(Q, 1));
+        // ... but a warp should walk at least ~32 tiles: the per-chunk setup (cursor starts, table
+        // ring, candidate compaction, one more list for k_merge) is not free (B: 489 tiles per query)
+        if (ix->opt_waves <= 0) splits = (int)std::min<int64_t>(splits, std::max<int64_t>(1, lp->n_tiles / (lp->warps * 32)));
     }
     splits = std::max(1, std::min(splits, max_splits));
     lp->tiles_per_chunk = (lp->n_tiles + splits * lp->warps - 1) / (splits * lp->warps);
