@@ -441,7 +441,7 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
         splits = (int)std::max<int64_t>(1, (want + Q - 1) / std::max<int64_t>(Q, 1));
         // ... but a warp should walk at least ~32 tiles: the per-chunk setup (cursor starts, table
         // ring, candidate compaction, one more list for k_merge) is not free (B: 489 tiles per query)
-        if (ix->opt_waves <= 0) splits = (int)std::min<int64_t>(splits, std::max<int64_t>(1, lp->n_tiles / (lp->warps * 32)));
+        if (ix->opt_waves <= 0) splits = (int)std::min<int64_t>(splits, std::max<int64_t>(1, (lp->n_tiles + lp->warps * 16) / (lp->warps * 32)));
     }
     splits = std::max(1, std::min(splits, max_splits));
     lp->tiles_per_chunk = (lp->n_tiles + splits * lp->warps - 1) / (splits * lp->warps);
