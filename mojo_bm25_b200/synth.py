@@ -4,9 +4,14 @@
 ever materialising documents.  Term rank r (0-based; term id == rank, id 0 = heaviest list) has
 document frequency  df_r = round(N * (1 - exp(-c / (r+1)^s)))  with c solved so that
 sum_r df_r = N * U (a saturating Zipf law: stop words approach df = N).  The doc ids of a column
-are a sorted stratified-uniform sample of size df_r from [0, N): posting i is drawn uniformly from
+are a sorted STRATIFIED-uniform sample of size df_r from [0, N): posting i is drawn uniformly from
 the i-th of df_r equal strata, which yields strictly increasing ids in O(nnz) fully vectorised
-work (on the GPU for the large configs).  Weights follow the bm25s "lucene" formula of the
+work (on the GPU for the large configs).  NOTE: this is more regular than the uniform sample
+without replacement SURVEY.md 8d names -- every document tile receives the same number of postings
+of a term (+-1), the friendliest case for a document-range-tiled kernel.  ``clustered=True`` is
+the hard counterpart: every term gets its own bursty density over the document range (64 segments
+with Gamma(0.3)-distributed weights, so a few segments hold most of the term's postings and many
+hold almost none); DESIGN.md reports both.  Weights follow the bm25s "lucene" formula of the
 bundled index (reference animal_index_bm25/data.csc.index.npy):
     w = idf_r * tf / (tf + k1 * (1 - b + b * dl_d / avgdl)),  idf_r = ln((N - df_r + .5)/(df_r + .5) + 1)
 with dl_d ~ clip(round(lognormal(ln 1.5U, 0.5)), 8, 512) and tf ~ geometric(p = 0.7).
@@ -57,9 +62,33 @@ def zipf_doc_freqs(n_docs: int, n_terms: int, mean_unique: float, s: float = 1.0
     return np.clip(df, 0, n_docs)
 
 
+def _clustered_quantiles(q: torch.Tensor, col: torch.Tensor, seed: int, n_seg: int = 64) -> torch.Tensor:
+    """Map the stratified quantiles q in [0,1) of the postings (term ``col``) through a per-term
+    piecewise-linear inverse CDF over ``n_seg`` equal document segments whose weights are
+    Gamma(0.3) draws, hashed from (seed, term, segment) so that no per-term table is stored."""
+    dev = q.device
+    seg = torch.arange(n_seg, device=dev, dtype=torch.int64)
+
+    def weights(c):  # [n, n_seg] float64, deterministic in (seed, c, seg)
+        h = (c[:, None] * 1_000_003 + seg[None, :] * 7_919 + seed * 104_729 + 12_345) % 2_147_483_647
+        u = ((h * 48_271) % 2_147_483_647).to(torch.float64) / 2_147_483_647.0
+        return torch.clamp(u, 1e-9, 1.0) ** (1.0 / 0.3) + 1e-4  # ~ Gamma(0.3)-like: heavy mass near 0
+
+    uniq, inv = torch.unique(col, return_inverse=True)
+    w = weights(uniq)
+    cdf = torch.cumsum(w / w.sum(dim=1, keepdim=True), dim=1)  # [n_uniq, n_seg]
+    cdf[:, -1] = 1.0
+    rows = cdf[inv]  # [n, n_seg]
+    k = torch.clamp((rows < q[:, None]).sum(dim=1), max=n_seg - 1)  # segment whose CDF range holds q
+    hi = rows.gather(1, k[:, None])[:, 0]
+    lo = torch.where(k > 0, rows.gather(1, torch.clamp(k - 1, min=0)[:, None])[:, 0], torch.zeros_like(hi))
+    frac = torch.clamp((q - lo) / torch.clamp(hi - lo, min=1e-18), 0.0, 1.0)
+    return (k.to(torch.float64) + frac) / n_seg
+
+
 def synth_index(n_docs: int, n_terms: int, mean_unique: float, s: float = 1.0, seed: int = 0,
                 device: str = "cpu", k1: float = 1.5, b: float = 0.75,
-                chunk: int = 1 << 26) -> SynthIndex:
+                chunk: int = 1 << 26, clustered: bool = False) -> SynthIndex:
     dev = torch.device(device)
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
@@ -90,6 +119,24 @@ def synth_index(n_docs: int, n_terms: int, mean_unique: float, s: float = 1.0, s
         hi = ((i + 1) * n_docs) // dfc
         u = torch.rand(end - start, generator=gen, device=dev, dtype=torch.float64)
         doc = lo + torch.clamp((u * (hi - lo).to(torch.float64)).to(torch.int64), max=(hi - lo - 1))
+        if clustered:
+            # bursty terms (df <= N/4; denser terms stay stratified): quantile -> per-term warped position,
+            # then made strictly increasing inside every term (ids are unique per term)
+            sub = chunk_sub = 1 << 20
+            for s0 in range(0, end - start, sub):
+                sl = slice(s0, min(end - start, s0 + sub))
+                sparse = dfc[sl] * 4 <= n_docs
+                if bool(sparse.any()):
+                    qq = (i[sl].to(torch.float64) + u[sl]) / dfc[sl].to(torch.float64)
+                    pos = _clustered_quantiles(qq[sparse], col[sl][sparse], seed)
+                    dsl = doc[sl]
+                    dsl[sparse] = torch.clamp((pos * n_docs).to(torch.int64), max=n_docs - 1)
+                    doc[sl] = dsl
+            big = int(n_docs) + int(nnz) + 1
+            e = doc - i + col * big                       # strictly increasing ids: d_i = max_{j<=i}(d_j - j) + i per term
+            doc = torch.cummax(e, dim=0).values - col * big + i
+            over = doc - (n_docs - dfc + i)               # ... and never beyond N - (df - i): shift the tail back
+            doc = doc - torch.clamp(over, min=0)
         u2 = torch.rand(end - start, generator=gen, device=dev, dtype=torch.float32).clamp_(min=1e-12)
         tf = 1.0 + torch.floor(torch.log(u2) / log1mp)
         wgt = idf[col] * tf / (tf + norm[doc])
@@ -152,11 +199,15 @@ WORKLOADS = {
 
 
 def make_workload(name: str, device: str = "cpu", index_seed: int = 0, query_seed: int = 1, scale: float = 1.0):
-    """Returns (SynthIndex, queries int32 [Q,T], k) of a named workload (optionally scaled down)."""
+    """Returns (SynthIndex, queries int32 [Q,T], k) of a named workload (optionally scaled down).
+    A trailing "c" (``"Bc"``, ``"10Mc"``) selects the clustered (bursty) variant of the index."""
+    clustered = name.endswith("c") and name[:-1] in WORKLOADS
+    if clustered:
+        name = name[:-1]
     cfg = dict(WORKLOADS[name])
     n_docs = max(64, int(cfg["n_docs"] * scale))
     n_terms = max(16, int(cfg["n_terms"] * scale))
-    idx = synth_index(n_docs, n_terms, cfg["mean_unique"], seed=index_seed, device=device)
+    idx = synth_index(n_docs, n_terms, cfg["mean_unique"], seed=index_seed, device=device, clustered=clustered)
     q = synth_queries(n_terms, cfg["n_queries"], cfg["n_query_terms"], r0=cfg.get("r0", 8), seed=query_seed,
                       device=device, poisson_mean=cfg.get("poisson_mean"), max_terms=cfg.get("max_terms", 16),
                       heavy_terms=cfg.get("heavy_terms", 0), heavy_range=cfg.get("heavy_range", 100))

@@ -89,7 +89,8 @@ def test_selfcheck_g4(engine, golden_dir):
 
 
 @pytest.mark.parametrize("workload,scale,k", [("tiny", 1.0, 10), ("B", 0.05, 10), ("B", 0.05, 100),
-                                              ("E", 0.03, 1000), ("C", 0.005, 100)])
+                                              ("E", 0.03, 1000), ("C", 0.005, 100), ("Bc", 0.05, 10),
+                                              ("10Mc", 0.01, 100)])
 def test_synthetic_workloads_against_oracle(engine, workload, scale, k):
     from mojo_bm25_b200 import synth
 
