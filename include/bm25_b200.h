@@ -14,6 +14,10 @@
  *     default stream) and return; *_host entry points synchronise before returning.
  *   - there is NO CPU fallback: without a CUDA device every entry point fails with
  *     BM25_ERR_NO_DEVICE.
+ *   - threading: a handle has ONE workspace.  Calls may come from any thread and use any stream:
+ *     enqueueing is serialised by a host mutex and a search that runs on a different stream than
+ *     the previous search of the same handle first waits (on the device) for that search, so the
+ *     searches of one handle never overlap.  Use one handle per stream for concurrent execution.
  *
  * Result order: score descending, ties by ascending document id.  Documents with no matching
  * posting have score +0.0 and fill the tail when fewer than k documents match (the reference
