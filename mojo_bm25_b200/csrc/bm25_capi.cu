@@ -419,6 +419,20 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
     // large k: the candidate buffer moves to global memory (see the kernel); it is then compacted by
     // radix select only, which needs cap > kSelectMin
     lp->cand_global = (k > kSelectMin && !ix->opt_cand_smem) ? 1 : 0;
+    // wide queries (T ~ 64) need so much cursor state that only two 8-warp CTAs fit on an SM: take the
+    // warp count (8, 7 or 6) that keeps the most warps resident (E: 3 x 7 = 21 instead of 2 x 8 = 16)
+    if (ix->opt_warps <= 0) {
+        int best_w = lp->warps, best_res = 0;
+        for (int w = lp->warps; w >= 6; --w) {
+            const size_t sm = score_smem(lp->tile_docs, lp->cand_global ? 0 : lp->cap, T, w) + 1024 + 1152;
+            const int res = (int)std::min<size_t>(ix->smem_per_sm / sm, 2048 / (w * 32)) * w;
+            if (res > best_res) {
+                best_res = res;
+                best_w = w;
+            }
+        }
+        lp->warps = best_w;
+    }
     // shrink the CTA (fewer warps, then smaller tiles) until it fits into shared memory
     const size_t hard = ix->smem_optin - 1024;
     for (;;) {
