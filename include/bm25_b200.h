@@ -39,7 +39,8 @@ extern "C" {
 #define BM25_ERR_UNSUPPORTED 4 /* valid request outside this build's limits (e.g. k) */
 #define BM25_ERR_OOM 5         /* host or device allocation failed                   */
 
-#define BM25_MAX_K 6144 /* largest supported top-k */
+#define BM25_MAX_K 65536 /* largest supported top-k */
+#define BM25_SMALL_K 6144 /* up to here the final merge sorts in shared memory; above, in global memory */
 #define BM25_MAX_DOCS (0x7fffffffLL - 65536) /* largest n_docs of one handle (int32 tile arithmetic) */
 
 typedef struct bm25_index bm25_index; /* opaque; owns the HBM-resident CSC arrays + workspace */
@@ -108,7 +109,8 @@ int bm25_index_get_timing(bm25_index* index, float* out_ms3);
  *               >= n_terms are rejected by the *_host entry point and ignored by this one.
  *   d_out_ids   [Q,k] int32   (doc id + doc_id_base)
  *   d_out_scores[Q,k] fp32
- * Requires 1 <= k <= min(n_docs, BM25_MAX_K) (the reference raises for k > n_docs). */
+ * Requires 1 <= k <= min(n_docs, BM25_MAX_K) (the reference raises for k > n_docs).  k above
+ * BM25_SMALL_K takes a slower, global-memory final merge. */
 int bm25_search(bm25_index* index, const int32_t* d_queries, int64_t Q, int64_t T, int k,
                 int32_t* d_out_ids, float* d_out_scores, void* cuda_stream);
 

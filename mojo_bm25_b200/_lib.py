@@ -9,7 +9,8 @@ import os
 from . import build as _build
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_OOM = 0, 1, 2, 3, 4, 5
-MAX_K = 6144
+MAX_K = 65536
+SMALL_K = 6144
 
 SYMBOLS = [
     "bm25_index_create", "bm25_index_create_device", "bm25_index_destroy", "bm25_index_get_info",

@@ -457,6 +457,7 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
         // ring, candidate compaction, one more list for k_merge) is not free (B: 489 tiles per query)
         if (ix->opt_waves <= 0) splits = (int)std::min<int64_t>(splits, std::max<int64_t>(1, (lp->n_tiles + lp->warps * 16) / (lp->warps * 32)));
     }
+    if (k > BM25_SMALL_K && ix->opt_splits <= 0) splits = std::min(splits, 2);  // 2k-key candidate buffers per CTA
     splits = std::max(1, std::min(splits, max_splits));
     lp->tiles_per_chunk = (lp->n_tiles + splits * lp->warps - 1) / (splits * lp->warps);
     lp->n_chunks = (lp->n_tiles + lp->tiles_per_chunk - 1) / lp->tiles_per_chunk;
@@ -546,6 +547,32 @@ int launch_merge(const MergeArgs& m, int device, size_t smem_optin, cudaStream_t
     return BM25_OK;
 }
 
+// k_out above BM25_SMALL_K: global-memory merge.  `scratch` / `present` are stream-ordered allocations
+// of this call (cudaMallocAsync) -- a large-k merge is the rare call, not the steady path.
+int launch_merge_large(MergeArgs m, cudaStream_t st) {
+    const int64_t total = (int64_t)m.n_lists * m.k_in;
+    m.P = next_pow2(m.k_out);
+    m.n_pad = (total + 1) & ~(int64_t)1;
+    u64* scratch = nullptr;
+    unsigned char* present = nullptr;
+    const size_t bytes = (size_t)m.Q * (size_t)(m.n_pad + m.P) * 8;
+    if (cudaMallocAsync(&scratch, bytes, st) != cudaSuccess ||
+        cudaMallocAsync(&present, (size_t)m.Q * m.k_out, st) != cudaSuccess) {
+        cudaGetLastError();
+        if (scratch) cudaFreeAsync(scratch, st);
+        return fail(BM25_ERR_OOM, "cudaMallocAsync of %zu bytes of merge scratch failed", bytes);
+    }
+    m.scratch = scratch;
+    m.present_g = present;
+    k_merge_large<<<(unsigned)m.Q, kThreads, 0, st>>>(m);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    cudaFreeAsync(present, st);
+    if (e != cudaSuccess) return fail(BM25_ERR_CUDA, "k_merge_large launch failed: %s", cudaGetErrorString(e));
+    return BM25_OK;
+}
+
 int merge_P(int64_t total, int k_out) {
     if (total <= 8192) return std::max(next_pow2(total), next_pow2(k_out));
     return std::max(8192, next_pow2(2 * (int64_t)k_out));
@@ -631,7 +658,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     m.P = merge_P((int64_t)lp.splits * k, k);
     m.id_offset = ix->doc_id_base;
     m.fill = 1;
-    if ((rc = launch_merge(m, ix->device, ix->smem_optin, st))) return rc;
+    if ((rc = (k > BM25_SMALL_K ? launch_merge_large(m, st) : launch_merge(m, ix->device, ix->smem_optin, st)))) return rc;
     if (timing) {
         CU(cudaEventRecord(ix->ev[3], st));
         ix->ev_valid = true;
@@ -1041,6 +1068,7 @@ int bm25_merge_topk(const int32_t* d_ids, const float* d_scores, int n_lists, in
     m.P = merge_P((int64_t)n_lists * k_in, k_out);
     m.id_offset = 0;
     m.fill = 0;
+    if (k_out > BM25_SMALL_K) return launch_merge_large(m, (cudaStream_t)cuda_stream);
     return launch_merge(m, device, prop.sharedMemPerBlockOptin, (cudaStream_t)cuda_stream);
 }
 

@@ -1417,6 +1417,10 @@ struct MergeArgs {
     int n_lists, k_in, k_out, P;
     int64_t id_offset;   // added to key doc ids on output (doc_id_base); 0 for shard merges
     int fill;            // 1: pad with zero-score docs 0,1,2.. not already present
+    // k_merge_large only: per query [n_pad] candidate keys followed by [P] keepers; k_out bytes of flags
+    u64* scratch;
+    unsigned char* present_g;
+    int64_t n_pad;
 };
 
 __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
@@ -1483,6 +1487,88 @@ __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_merge_large: the same merge for k_out above what k_merge sorts in shared memory (BM25_SMALL_K).
+// One CTA per query, everything in global memory (L2): the candidates are gathered into
+// scratch, a radix select isolates the k_out best (select_candidates), the keepers are sorted
+// with a bitonic sort in place, then unpacked / zero-filled like k_merge.  O(n) + O(k log^2 k) per
+// query -- the rare large-k call (the reference's _topk takes any k <= D, bm25_native.py:204-214).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_merge_large(const MergeArgs a) {
+    __shared__ int hist[264];
+    __shared__ int s_n, s_valid;
+    __shared__ u64 s_theta;
+    const int tid = threadIdx.x;
+    const int64_t q = blockIdx.x;
+    const int total = a.n_lists * a.k_in;
+    const int keep = a.k_out;
+    const CtaGroup grp{kThreads, tid};
+    u64* cand = a.scratch + q * (a.n_pad + a.P);
+    u64* kept = cand + a.n_pad;
+    unsigned char* present = a.present_g + q * keep;
+    if (tid == 0) {
+        s_valid = 0;
+        s_n = 0;
+    }
+    for (int i = tid; i < keep; i += kThreads) present[i] = 0;
+    __syncthreads();
+    int local = 0;
+    for (int e = tid; e < total; e += kThreads) {
+        u64 key;
+        if (a.keys) {
+            key = a.keys[q * total + e];
+        } else {
+            const int l = e / a.k_in, r = e - l * a.k_in;
+            const int64_t off = (int64_t)l * a.list_stride + q * a.k_in + r;
+            const int32_t id = a.in_ids[off];
+            key = id < 0 ? 0ull : make_key(a.in_scores[off], (uint32_t)id);
+        }
+        cand[e] = key;
+        if (key) ++local;
+    }
+    if (local) atomicAdd(&s_valid, local);
+    __syncthreads();
+    const int n_valid = s_valid;
+    int nk;
+    if (n_valid > keep) {
+        select_candidates(cand, total, keep, kept, hist, &s_n, &s_theta, false, grp);
+        nk = keep;
+    } else {  // everything valid is a keeper
+        for (int e = tid; e < total; e += kThreads) {
+            const u64 key = cand[e];
+            if (key) kept[atomicAdd(&s_n, 1)] = key;
+        }
+        nk = n_valid;
+    }
+    __syncthreads();
+    for (int i = nk + tid; i < a.P; i += kThreads) kept[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(kept, a.P, grp);
+    int cnt = 0;
+    for (int i = tid; i < keep; i += kThreads) {
+        const u64 key = kept[i];
+        if (key != 0) {
+            ++cnt;
+            const uint32_t d = key_doc(key);
+            a.out_ids[q * keep + i] = (int32_t)((int64_t)d + a.id_offset);
+            a.out_scores[q * keep + i] = key_score(key);
+            if (a.fill && d < (uint32_t)keep) present[d] = 1;
+        }
+    }
+    __syncthreads();
+    if (a.fill && tid == 0 && nk < keep) {
+        int pos = nk;
+        for (int d = 0; pos < keep; ++d) {
+            if (!present[d]) {
+                a.out_ids[q * keep + pos] = (int32_t)((int64_t)d + a.id_offset);
+                a.out_scores[q * keep + pos] = 0.f;
+                ++pos;
+            }
+        }
+    }
+    (void)cnt;
 }
 
 // ---------------------------------------------------------------------------------------------

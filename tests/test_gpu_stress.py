@@ -100,25 +100,43 @@ def test_general_path_with_overflow_rounds_and_shared_thresholds():
     assert np.array_equal(ids[0], zero_docs)
 
 
-def test_k_above_the_supported_maximum_is_a_value_error():
-    """BM25v._topk accepts any k <= n_docs (bm25_native.py:204-214); this build supports
-    k <= BM25_MAX_K and says so with a ValueError instead of an internal error."""
-    from mojo_bm25_b200 import _lib, engine
-    from mojo_bm25_b200.bm25_native import BM25v
+def test_large_k_uses_the_global_memory_merge_and_the_maximum_is_a_value_error():
+    """BM25v._topk accepts any k <= n_docs (bm25_native.py:204-214).  Up to BM25_SMALL_K the final
+    merge sorts in shared memory, above it in global memory (k_merge_large); above BM25_MAX_K the
+    call is rejected with a ValueError instead of an internal error."""
     import scipy.sparse as sp
+    from mojo_bm25_b200 import _lib, engine, sharded
+    from mojo_bm25_b200.bm25_native import BM25v
 
-    n_docs = _lib.MAX_K + 500
-    m = sp.random(n_docs, 5, density=0.3, format="csc", dtype=np.float32, random_state=np.random.RandomState(0))
+    rng = np.random.default_rng(2)
+    n_docs = _lib.MAX_K + 3000
+    m = sp.random(n_docs, 8, density=0.25, format="csc", dtype=np.float32, random_state=np.random.RandomState(0),
+                  data_rvs=lambda n: (0.01 + rng.random(n)).astype(np.float32))
     m.sort_indices()
-    m.data = np.abs(m.data) + 0.01
-    index = engine.DeviceIndex(m.indptr, m.indices, m.data, n_docs=n_docs)
-    q = np.array([[0, 1]], np.int32)
-    ids, sc = index.search(q, _lib.MAX_K)  # the maximum itself works
-    dense = c_oracle.scores_dense(m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data, n_docs, q[0])
-    orc.check_topk_against_dense(ids[0], sc[0], dense, _lib.MAX_K, exact=True)
+    indptr, indices, data = m.indptr.astype(np.int32), m.indices.astype(np.int32), m.data
+    index = engine.DeviceIndex(indptr, indices, data, n_docs=n_docs)
+    q = np.array([[0, 1, -1], [2, 3, 7], [5, -1, -1]], np.int32)
+    for k in (_lib.SMALL_K, _lib.SMALL_K + 1, 10_000, 30_000, _lib.MAX_K):
+        ids, sc = index.search(q, k)
+        for i in range(len(q)):
+            dense = c_oracle.scores_dense(indptr, indices, data, n_docs, q[i])
+            orc.check_topk_against_dense(ids[i], sc[i], dense, k, exact=True)
+            same = sc[i][1:] == sc[i][:-1]
+            assert np.all(ids[i][1:][same] > ids[i][:-1][same])
     with pytest.raises(ValueError, match="BM25_MAX_K"):
         index.search(q, _lib.MAX_K + 1)
     model = BM25v()
     model.index(m, np.ones(n_docs, np.int32))
     with pytest.raises(ValueError):
         model.search(q, top_k=_lib.MAX_K + 1)
+    # the shard merge takes the same path for a large k_out
+    import torch
+
+    k = 9000
+    parts = orc.partition_csc_by_doc_range(indptr, indices, data, n_docs, 3)
+    shards = [engine.DeviceIndex(p, i_, d, n_docs=nd, doc_id_base=base) for p, i_, d, nd, base in parts]
+    s_ = sharded.DocShardedSearcher.from_index(shards, k)
+    gi, gs = s_.search(torch.from_numpy(q).cuda())
+    torch.cuda.synchronize()
+    wi, ws = index.search(q, k)
+    assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(gs.cpu().numpy().view(np.uint32), ws.view(np.uint32))
