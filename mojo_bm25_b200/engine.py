@@ -17,6 +17,19 @@ def _as_c(a, dtype) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+def _as_i32(a, what: str) -> np.ndarray:
+    """int32 view/copy of an integer array; values that do not fit raise instead of wrapping
+    (bm25s writes int32 arrays, scipy may hand over int64 indptr/indices)."""
+    a = np.asarray(a)
+    if a.dtype != np.int32:
+        if a.dtype.kind not in "iu":
+            raise ValueError(f"{what} must be an integer array (got {a.dtype})")
+        if a.size and (int(a.max()) > np.iinfo(np.int32).max or int(a.min()) < np.iinfo(np.int32).min):
+            raise ValueError(f"{what} holds values outside int32: shard the index by document range "
+                             "(one handle holds fewer than 2^31 postings)")
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
 def _ptr(a: np.ndarray):
     return ctypes.c_void_p(a.ctypes.data)
 
@@ -30,8 +43,8 @@ class DeviceIndex:
 
     def __init__(self, indptr, indices, data, n_docs: int, device: int = 0, doc_id_base: int = 0):
         lib = _lib.load()
-        indptr = _as_c(indptr, np.int32)
-        indices = _as_c(indices, np.int32)
+        indptr = _as_i32(indptr, "indptr")
+        indices = _as_i32(indices, "indices")
         data = _as_c(data, np.float32)
         if indptr.ndim != 1 or indptr.shape[0] < 1:
             raise ValueError("indptr must be a 1-D array with at least one element")

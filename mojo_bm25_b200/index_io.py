@@ -110,6 +110,9 @@ def load_index(path: str, load_corpus: bool = False, mmap: bool = False) -> Disk
         vocab = json.load(f)
     if "num_docs" not in params:
         raise ValueError("params.index.json lacks num_docs")
+    for name, arr in (("indptr", indptr), ("indices", indices)):
+        if arr.dtype != np.int32 and arr.size and (int(arr.max()) > np.iinfo(np.int32).max or int(arr.min()) < 0):
+            raise ValueError(f"{name} of {path} does not fit int32; shard the index by document range")
     indptr = np.ascontiguousarray(indptr, dtype=np.int32)
     indices = np.ascontiguousarray(indices, dtype=np.int32)
     data = np.ascontiguousarray(data, dtype=np.float32)

@@ -68,3 +68,17 @@ def test_argument_validation_happens_before_device_use():
     assert b"NULL" in lib.bm25_last_error()
     rc = lib.bm25_search(None, None, 1, 1, 1, None, None, None)
     assert rc == _lib.ERR_INVALID
+
+
+def test_int64_index_arrays_are_range_checked_before_the_int32_cast():
+    """int64 indptr / indices must not wrap silently (no GPU needed: the check runs
+    before the library is called)."""
+    from mojo_bm25_b200 import engine
+
+    big = np.array([0, 2 ** 31 + 5], np.int64)
+    with pytest.raises(ValueError, match="int32"):
+        engine.DeviceIndex(big, np.zeros(1, np.int64), np.ones(1, np.float32), n_docs=10)
+    with pytest.raises(ValueError, match="int32"):
+        engine.DeviceIndex(np.array([0, 1], np.int64), np.array([2 ** 40], np.int64), np.ones(1, np.float32), n_docs=10)
+    with pytest.raises(ValueError, match="integer"):
+        engine.DeviceIndex(np.array([0.0, 1.0]), np.array([0], np.int64), np.ones(1, np.float32), n_docs=10)
