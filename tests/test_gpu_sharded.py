@@ -101,3 +101,33 @@ def test_two_searches_on_different_streams_share_one_workspace_safely():
         assert torch.equal(xa[0], ra[0]) and torch.equal(xa[1], ra[1])
         assert torch.equal(xb[0], rb[0]) and torch.equal(xb[1], rb[1])
         assert np.array_equal(hid, ra[0].cpu().numpy())
+
+
+def test_concurrent_host_threads_on_one_handle():
+    """Several Python threads calling the host entry point of ONE handle (ctypes releases the GIL):
+    the mutex + stream ordering serialise them; every thread gets the serial answer."""
+    import threading
+    from mojo_bm25_b200 import engine, synth
+
+    idx, q, k = synth.make_workload("B", scale=0.05)
+    indptr, indices, data = idx.numpy()
+    qn = q.numpy()
+    index = engine.DeviceIndex(indptr, indices, data, n_docs=idx.n_docs)
+    parts = [qn[i::4] for i in range(4)]
+    want = [index.search(p, k) for p in parts]
+    errors = []
+
+    def work(i):
+        try:
+            for _ in range(15):
+                ids, sc = index.search(parts[i], k)
+                assert np.array_equal(ids, want[i][0]) and np.array_equal(sc.view(np.uint32), want[i][1].view(np.uint32))
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
