@@ -92,6 +92,9 @@ int bm25_index_get_info(const bm25_index* index, bm25_index_info* out);
  *   "cand_smem"      1: keep the candidate buffer in shared memory also for k > 256
  *   "heavy_min"      a term gets a row in the tile table when df*16 >= heavy_min * n_tiles (default 16,
  *                    i.e. one posting per document tile on average); lighter terms are walked by cursors
+ *   "generic_kernel" 1: use the any-T kernel also for queries of <= 32 term slots (A/B switch)
+ *   "no_query_sort" / "q_major" / "no_bulk_clear"   1: keep the batch order / query-major CTA order /
+ *                    vector-store tile clear (A/B switches)
  *   "poison"         1 (debug): fill workspace and shared memory with 0xff before every search
  *   "no_hot" / "no_priming" / "no_theta_share"   1: disable the hot-list epilogue / the load-time
  *                    threshold priming / the per-query threshold shared between CTAs (A/B switches)

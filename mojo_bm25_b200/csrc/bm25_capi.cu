@@ -166,7 +166,7 @@ struct bm25_index {
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
     int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_heavy_min = 0, opt_cand_smem = 0;
-    int opt_poison = 0, opt_no_bulk_clear = 0, opt_no_query_sort = 0, opt_generic_kernel = 0;
+    int opt_poison = 0, opt_no_bulk_clear = 0, opt_no_query_sort = 0, opt_generic_kernel = 0, opt_q_major = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace: one per handle; searches on different streams are ordered through ws_done
@@ -249,6 +249,24 @@ int finish_create(bm25_index* ix, const cudaDeviceProp& prop, const int32_t* d_i
         k_term_bounds<<<(unsigned)V, 128>>>(ix->d_tptr, ix->d_w, (int)V, ix->d_bounds);
         ++g_launches;
         CU(cudaGetLastError());
+        // long lists: exact order statistics over all their postings
+        std::vector<int32_t> big;
+        for (int64_t t = 0; t < V; ++t)
+            if (ix->h_indptr[t + 1] - ix->h_indptr[t] > kBoundSample) big.push_back((int32_t)t);
+        if (!big.empty() && !getenv("BM25_B200_SAMPLED_BOUNDS")) {
+            int32_t* d_big = nullptr;
+            if (cudaMalloc(&d_big, big.size() * 4) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(BM25_ERR_OOM, "cudaMalloc of the long-term list failed");
+            }
+            cudaMemcpy(d_big, big.data(), big.size() * 4, cudaMemcpyHostToDevice);
+            const int grid = (int)std::min<size_t>(big.size(), (size_t)ix->sm_count * 8);
+            k_term_bounds_exact<<<grid, 256>>>(ix->d_tptr, ix->d_w, d_big, (int)big.size(), ix->d_bounds);
+            ++g_launches;
+            cudaError_t e = cudaDeviceSynchronize();
+            cudaFree(d_big);
+            if (e != cudaSuccess) return fail(BM25_ERR_CUDA, "k_term_bounds_exact failed: %s", cudaGetErrorString(e));
+        }
     }
     CU(cudaDeviceSynchronize());
     return BM25_OK;
@@ -644,6 +662,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.general = lp.general;
     a.no_hot = ix->opt_no_hot;
     a.poison = ix->opt_poison;
+    a.sp_major = ix->opt_q_major ? 0 : 1;
     a.bulk_clear = ix->opt_no_bulk_clear ? 0 : 1;
     if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
@@ -897,6 +916,8 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
     } else if (!strcmp(name, "heavy_min")) {
         if (value < 0 || value > (1 << 28)) return fail(BM25_ERR_INVALID, "heavy_min out of range");
         ix->opt_heavy_min = (int)value;
+    } else if (!strcmp(name, "q_major")) {
+        ix->opt_q_major = value ? 1 : 0;
     } else if (!strcmp(name, "generic_kernel")) {
         ix->opt_generic_kernel = value ? 1 : 0;
     } else if (!strcmp(name, "no_query_sort")) {

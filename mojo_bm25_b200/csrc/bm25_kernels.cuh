@@ -380,6 +380,7 @@ struct SearchArgs {
     int general;                           // 1: zero-score docs compete (weights may be <= 0)
     int no_hot;                            // 1: always use the dense tile scan (A/B switch)
     int poison;                            // 1 (debug): fill the dynamic shared memory with 0xff before use
+    int sp_major;                          // 1: CTA index = split * Q + query slot (else query slot * splits + split)
     int bulk_clear;                        // 1: clear the score tile with st.bulk (UMEMSETS) instead of vector stores
 };
 
@@ -784,8 +785,11 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int qslot = blockIdx.x / a.splits;
-    const int sp = blockIdx.x - qslot * a.splits;
+    // split-major CTA order: the CTAs of the first document range of EVERY query come first, so the
+    // later ranges of a query start from the threshold its earlier ranges published (theta_q), and
+    // neighbouring CTAs walk the same document range of neighbouring (same heaviest term) queries
+    const int sp = a.sp_major ? blockIdx.x / a.Q : blockIdx.x % a.splits;
+    const int qslot = a.sp_major ? blockIdx.x - sp * a.Q : blockIdx.x / a.splits;
     const int q = a.qperm ? __ldg(a.qperm + qslot) : qslot;
     const int chunk = sp * NCW + warp;
 
@@ -1153,8 +1157,11 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int qslot = blockIdx.x / a.splits;
-    const int sp = blockIdx.x - qslot * a.splits;
+    // split-major CTA order: the CTAs of the first document range of EVERY query come first, so the
+    // later ranges of a query start from the threshold its earlier ranges published (theta_q), and
+    // neighbouring CTAs walk the same document range of neighbouring (same heaviest term) queries
+    const int sp = a.sp_major ? blockIdx.x / a.Q : blockIdx.x % a.splits;
+    const int qslot = a.sp_major ? blockIdx.x - sp * a.Q : blockIdx.x / a.splits;
     const int q = a.qperm ? __ldg(a.qperm + qslot) : qslot;
     const int chunk = sp * NCW + warp;
 
@@ -1596,6 +1603,67 @@ __global__ void __launch_bounds__(128) k_term_bounds(const int2* __restrict__ tp
     if (tid < kBoundLevels) {
         const int r = 1 << tid;
         out[tid] = r <= m ? ord_to_f32((uint32_t)(buf[r - 1] >> 32)) : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_term_bounds_exact (load time): the same order statistics for the terms with MORE than
+// kBoundSample postings, over ALL their postings (k_term_bounds only sees the first kBoundSample,
+// whose 2^l-th largest weight is a percentile of the term, not its 2^l-th largest weight -- a much
+// looser threshold for the long lists that matter).  One CTA per term: a 4-pass 8-bit radix select
+// finds the kBoundSample-th largest weight exactly (weights are > 0: their bit patterns order like
+// the values), one more pass collects the larger ones, a bitonic sort orders them.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_term_bounds_exact(const int2* __restrict__ tptr, const float* __restrict__ w,
+                                                           const int32_t* __restrict__ big_terms, int n_big,
+                                                           float* __restrict__ bounds) {
+    __shared__ u64 buf[kBoundSample];
+    __shared__ int hist[256];
+    __shared__ unsigned s_prefix;
+    __shared__ int s_need, s_cnt;
+    const int tid = threadIdx.x;
+    for (int bi = blockIdx.x; bi < n_big; bi += gridDim.x) {
+        const int t = big_terms[bi];
+        const int lo = tptr[t].x, hi = tptr[t].y;
+        if (tid == 0) {
+            s_prefix = 0u;
+            s_need = kBoundSample;
+            s_cnt = 0;
+        }
+        unsigned known = 0u;
+        __syncthreads();
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            hist[tid] = 0;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+            for (int i = lo + tid; i < hi; i += 256) {
+                const unsigned b = __float_as_uint(__ldg(w + i));
+                if ((b & known) == prefix) atomicAdd(&hist[(b >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (tid == 0) {  // the digit whose bucket holds the s_need-th largest of the remaining candidates
+                int need = s_need, d = 255;
+                for (; d > 0; --d) {
+                    if (hist[d] >= need) break;
+                    need -= hist[d];
+                }
+                s_need = need;
+                s_prefix = prefix | ((unsigned)d << shift);
+            }
+            known |= 0xffu << shift;
+            __syncthreads();
+        }
+        const unsigned tstar = s_prefix;  // the kBoundSample-th largest weight (bit pattern)
+        for (int i = lo + tid; i < hi; i += 256) {
+            const unsigned b = __float_as_uint(__ldg(w + i));
+            if (b > tstar) buf[atomicAdd(&s_cnt, 1)] = (u64)b << 32;  // fewer than kBoundSample of them
+        }
+        __syncthreads();
+        for (int i = s_cnt + tid; i < kBoundSample; i += 256) buf[i] = (u64)tstar << 32;  // ties at the cut
+        __syncthreads();
+        bitonic_sort_desc(buf, kBoundSample, CtaGroup{256, tid});
+        if (tid < kBoundLevels) bounds[(int64_t)t * kBoundLevels + tid] = __uint_as_float((unsigned)(buf[(1 << tid) - 1] >> 32));
+        __syncthreads();
     }
 }
 
