@@ -316,7 +316,7 @@ def timed_steps(ctx, step, steps, warmup):
 
 def kernel_split(ctx, indexes, step, steps):
     """Second, separate pass (its waits are NOT inside the timed loop of `value`): per-kernel device
-    time from the library's own events on the launching stream -> mean (segments + query order,
+    time from the library's own events on the launching stream -> median (segments + query order,
     score + top-k, merge) ms per step, summed over this rank's shards."""
     import numpy as np
 
@@ -329,7 +329,7 @@ def kernel_split(ctx, indexes, step, steps):
         rows.append(tuple(map(sum, zip(*[ix.last_timing_ms() for ix in indexes]))))
     for ix in indexes:
         ix.set_option("timing", 0)
-    return np.array(rows).mean(axis=0)
+    return np.median(np.array(rows), axis=0)  # median: one slow launch (e.g. a clock ramp after the sync) must not move it
 
 
 def roofline_record(ctx, posting_bytes, km, batch_bytes, ms_per_step):
@@ -461,7 +461,7 @@ def run_doc_shard(ctx, workload, steps, warmup, scale=1.0, parity_queries=4, wan
         step()
         parts.append(searcher.last_timing_ms())
     searcher.timing = False
-    local_ms, gather_ms, merge_ms = (ctx.max_over_ranks(float(x)) for x in np.array(parts).mean(axis=0))
+    local_ms, gather_ms, merge_ms = (ctx.max_over_ranks(float(x)) for x in np.median(np.array(parts), axis=0))
     km = kernel_split(ctx, indexes, step, steps)
     posting_bytes = sum(ix.posting_bytes(qn, 0) for ix in indexes)
     # e2e: pinned queries -> H2D -> local search(es) -> all-gather -> merge -> D2H of the result
