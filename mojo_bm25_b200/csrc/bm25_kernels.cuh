@@ -6,18 +6,22 @@
 // and select the top-k by (score desc, doc id asc).
 //
 // Kernels:
-//   k_relayout      load time: CSC postings -> padded, 16-byte aligned posting lists
-//   k_build_table   load time: per (heavy term, document tile) first-posting table
-//   k_term_bounds   load time: per-term weight order statistics (threshold priming)
-//   k_segments      per (query, term): threshold priming; cursor starts of the light terms for
-//                   every document chunk (binary search on doc id inside the term's posting list)
-//   k_score_topk    one warp per (query, document chunk): private shared-memory score tile,
-//                   in-order accumulation (heavy terms: table-addressed 16-byte vector loads;
-//                   light terms: cursors with cp.async-prefetched heads), fused threshold-pruned
-//                   top-k into the CTA's candidate buffer; emits k 64-bit keys per (query, CTA)
-//   k_merge         per query: merge candidate lists (tile ranges or GPU shards), zero-score
-//                   fill, unpack to (doc id, score)
-//   k_validate_*    load-time canonical-form checks of the CSC arrays
+//   k_relayout           load time: CSC postings -> padded, 16-byte aligned, sentinel-terminated posting lists
+//   k_build_table        load time: per (heavy term, document tile) first-posting table
+//   k_term_bounds[_exact] load time: per-term weight order statistics (threshold priming)
+//   k_segments           per (query, term): threshold priming; cursor starts of the light terms for
+//                        every document chunk (binary search on doc id inside the term's posting list)
+//   k_query_order        per batch: queries with the same heaviest term become neighbours (L2 sharing)
+//   k_score_topk_s       (query width <= 32) / k_score_topk (any width): one warp per (query, document
+//                        chunk): private shared-memory score tile, in-order accumulation (heavy terms:
+//                        table-addressed 16-byte vector loads, PTX read-modify-write; light terms:
+//                        cursors with cp.async-prefetched heads), hot-list tile end with st.bulk
+//                        clear, threshold-pruned top-k into the CTA's candidate buffer; emits k
+//                        64-bit keys per (query, CTA)
+//   k_merge[_large]      per query: merge candidate lists (tile ranges or GPU shards), zero-score
+//                        fill, unpack to (doc id, score); _large: k above BM25_SMALL_K, in global memory
+//   k_scores_dense       parity/debug: dense [Q, n_docs] score slab
+//   k_validate_*         load-time canonical-form checks of the CSC arrays
 #pragma once
 
 #include <cuda_runtime.h>
