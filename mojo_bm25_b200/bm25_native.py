@@ -10,7 +10,7 @@ from typing import Tuple
 
 import numpy as np
 
-from .engine import DeviceIndex
+from .engine import DeviceIndex, open_index
 
 
 class BM25v:
@@ -41,8 +41,9 @@ class BM25v:
         self.num_docs = int(doc_toks.shape[0])
         if self._index is not None:
             self._index.close()
-        self._index = DeviceIndex(doc_toks.indptr, doc_toks.indices, doc_toks.data, self.num_docs,
-                                  device=self.device)
+        # one handle, or several document-range handles when the matrix has >= 2^31 postings (int64 indptr)
+        self._index = open_index(doc_toks.indptr, doc_toks.indices, doc_toks.data, self.num_docs,
+                                 device=self.device)
 
     # bm25_native.py:76-103
     def search(self, queries, top_k: int = 100) -> Tuple[np.ndarray, np.ndarray]:

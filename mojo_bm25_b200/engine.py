@@ -176,6 +176,86 @@ class DeviceIndex:
         return int(out.value)
 
 
+class SplitDeviceIndex:
+    """A CSC index with more postings than one handle addresses (offsets are int32: < 2^31 postings
+    per handle) -- e.g. an int64-``indptr`` matrix -- held on ONE device as several document-range
+    handles.  Built on the host: the document range is cut so that every part has at most
+    ``max_postings`` postings, each part becomes a ``DeviceIndex`` with local doc ids and its
+    ``doc_id_base``; ``search`` runs every part and merges with ``bm25_merge_topk`` (the same path
+    the multi-GPU document sharding takes)."""
+
+    def __init__(self, indptr, indices, data, n_docs: int, device: int = 0, max_postings: int = (1 << 31) - (1 << 24)):
+        indptr = np.asarray(indptr)
+        if indptr.dtype.kind not in "iu":
+            raise ValueError("indptr must be an integer array")
+        indptr = indptr.astype(np.int64, copy=False)
+        indices = np.asarray(indices)
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        n_docs, n_terms, nnz = int(n_docs), indptr.shape[0] - 1, int(indptr[-1])
+        if indices.shape[0] != nnz or data.shape[0] != nnz:
+            raise ValueError("indptr[-1] must equal the number of postings")
+        if indices.size and (int(indices.max()) >= n_docs or int(indices.min()) < 0):
+            raise ValueError("document id outside [0, n_docs)")
+        # cut the document range where the cumulative posting count crosses multiples of max_postings
+        per_doc = np.bincount(indices, minlength=n_docs).astype(np.int64)
+        cum = np.cumsum(per_doc)
+        cuts, start = [0], 0
+        while start < n_docs:
+            base = cum[start - 1] if start else 0
+            end = int(np.searchsorted(cum, base + max_postings, side="right"))
+            end = max(end, start + 1)  # a single document never exceeds the limit in practice
+            cuts.append(min(end, n_docs))
+            start = cuts[-1]
+        self.parts, self.n_docs, self.n_terms, self.device = [], n_docs, n_terms, int(device)
+        col_ends = indptr[1:]
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            sel = np.flatnonzero((indices >= lo) & (indices < hi))
+            col = np.searchsorted(col_ends, sel, side="right")  # column of every selected posting
+            sub_ptr = np.zeros(n_terms + 1, dtype=np.int64)
+            np.cumsum(np.bincount(col, minlength=n_terms), out=sub_ptr[1:])
+            self.parts.append(DeviceIndex(sub_ptr, (indices[sel] - lo).astype(np.int32), data[sel], hi - lo,
+                                          device=device, doc_id_base=lo))
+        self._searchers = {}
+
+    def close(self):
+        for p in self.parts:
+            p.close()
+        self.parts = []
+
+    def search(self, queries: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        """Host-buffer search like ``DeviceIndex.search``."""
+        import torch
+
+        from .sharded import DocShardedSearcher
+
+        q = _as_c(queries, np.int32)
+        if q.ndim != 2:
+            raise ValueError("queries must be 2-D [Q, T]")
+        if k > self.n_docs:
+            raise ValueError(f"kth(=-{k}) out of bounds ({self.n_docs})")
+        if q.size and int(q.max(initial=-1)) >= self.n_terms:
+            raise ValueError("The maximum token ID in the query is higher than the number of tokens in the index.")
+        if q.shape[1] == 0:
+            q = np.full((q.shape[0], 1), -1, np.int32)
+        s = self._searchers.get(int(k))
+        if s is None:
+            s = self._searchers[int(k)] = DocShardedSearcher.from_index(self.parts, int(k))
+        dev = torch.device("cuda", self.device)
+        ids, sc = s.search(torch.from_numpy(q).to(dev))
+        torch.cuda.synchronize(dev)
+        return ids.cpu().numpy(), sc.cpu().numpy()
+
+
+def open_index(indptr, indices, data, n_docs: int, device: int = 0, doc_id_base: int = 0):
+    """``DeviceIndex`` when the postings fit one handle, else ``SplitDeviceIndex``."""
+    nnz = int(np.asarray(indptr)[-1]) if len(indptr) else 0
+    if nnz < (1 << 31) - (1 << 24):
+        return DeviceIndex(indptr, indices, data, n_docs, device=device, doc_id_base=doc_id_base)
+    if doc_id_base:
+        raise ValueError("doc_id_base is not supported for an index that is split into several handles")
+    return SplitDeviceIndex(indptr, indices, data, n_docs, device=device)
+
+
 def merge_topk_device(ids, scores, k_out: int, stream: Optional[int] = None, list_stride: int = 0,
                       n_lists: Optional[int] = None, n_queries: Optional[int] = None, k_in: Optional[int] = None):
     """Merge all-gathered shard results into the global top-k (bm25_merge_topk).

@@ -131,3 +131,25 @@ def test_concurrent_host_threads_on_one_handle():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_split_device_index_equals_one_handle():
+    """An index too large for one handle's int32 posting offsets (int64 indptr) is held as several
+    document-range handles on one device (engine.SplitDeviceIndex); forced here with a tiny limit."""
+    from mojo_bm25_b200 import engine, synth
+
+    idx, q, k = synth.make_workload("B", scale=0.03)
+    indptr, indices, data = idx.numpy()
+    qn = q.numpy()[:40]
+    whole = engine.DeviceIndex(indptr, indices, data, n_docs=idx.n_docs)
+    want = whole.search(qn, 25)
+    split = engine.SplitDeviceIndex(indptr.astype(np.int64), indices.astype(np.int64), data, idx.n_docs,
+                                    max_postings=idx.nnz // 5 + 7)
+    assert len(split.parts) >= 5 and sum(p.n_docs for p in split.parts) == idx.n_docs
+    got = split.search(qn, 25)
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1].view(np.uint32), want[1].view(np.uint32))
+    got = split.search(qn, 3)  # another k: its own searcher
+    assert np.array_equal(got[0], want[0][:, :3])
+    with pytest.raises(ValueError):
+        split.search(np.array([[idx.n_terms]], np.int32), 3)
+    assert isinstance(engine.open_index(indptr, indices, data, idx.n_docs), engine.DeviceIndex)
