@@ -155,6 +155,7 @@ struct bm25_index {
     // the re-bucketed index (layout documented in bm25_kernels.cuh)
     int64_t nnz_padded = 0;
     int2* d_tptr = nullptr;         // [n_terms] {start, end} of every term in the padded arrays
+    float2* d_wrange = nullptr;     // [n_terms] {smallest, largest} weight of the term
     int32_t* d_ids = nullptr;       // [nnz_padded]
     float* d_w = nullptr;           // [nnz_padded]
     int32_t* d_term_row = nullptr;  // [n_terms] tile-table row or -1
@@ -166,7 +167,7 @@ struct bm25_index {
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
     int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_heavy_min = 0, opt_cand_smem = 0;
-    int opt_poison = 0, opt_no_bulk_clear = 0, opt_no_query_sort = 0, opt_generic_kernel = 0, opt_q_major = 0;
+    int opt_poison = 0, opt_no_bulk_clear = 0, opt_no_query_sort = 0, opt_generic_kernel = 0, opt_q_major = 0, opt_no_epoch = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace: one per handle; searches on different streams are ordered through ws_done
@@ -229,14 +230,15 @@ int finish_create(bm25_index* ix, const cudaDeviceProp& prop, const int32_t* d_i
     if (cudaMalloc(&ix->d_tptr, (size_t)std::max<int64_t>(V, 1) * sizeof(int2)) != cudaSuccess ||
         cudaMalloc(&ix->d_ids, (size_t)(pos + 4) * 4) != cudaSuccess ||
         cudaMalloc(&ix->d_w, (size_t)(pos + 4) * 4) != cudaSuccess ||
-        cudaMalloc(&ix->d_term_row, (size_t)std::max<int64_t>(V, 1) * 4) != cudaSuccess) {
+        cudaMalloc(&ix->d_term_row, (size_t)std::max<int64_t>(V, 1) * 4) != cudaSuccess ||
+        cudaMalloc(&ix->d_wrange, (size_t)std::max<int64_t>(V, 1) * sizeof(float2)) != cudaSuccess) {
         cudaGetLastError();
         return fail(BM25_ERR_OOM, "cudaMalloc of the index (%lld postings) failed", (long long)ix->nnz);
     }
     CU(cudaMemcpy(ix->d_tptr, tptr.data(), (size_t)V * sizeof(int2), cudaMemcpyHostToDevice));
     if (V > 0 && pos > 0) {
         const int grid = (int)std::min<int64_t>(V, (int64_t)ix->sm_count * 16);
-        k_relayout<<<grid, 128>>>(d_indptr_raw, d_ids_raw, d_w_raw, ix->d_tptr, (int)V, ix->d_ids, ix->d_w);
+        k_relayout<<<grid, 128>>>(d_indptr_raw, d_ids_raw, d_w_raw, ix->d_tptr, (int)V, ix->d_ids, ix->d_w, ix->d_wrange);
         ++g_launches;
         CU(cudaGetLastError());
     }
@@ -664,6 +666,8 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.poison = ix->opt_poison;
     a.sp_major = ix->opt_q_major ? 0 : 1;
     a.bulk_clear = ix->opt_no_bulk_clear ? 0 : 1;
+    a.wrange = ix->d_wrange;
+    a.no_epoch = ix->opt_no_epoch;
     if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
     MergeArgs m{};
@@ -850,6 +854,7 @@ int bm25_index_destroy(bm25_index* ix) {
         DeviceGuard g(ix->device);
         if (ix->d_tptr) cudaFree(ix->d_tptr);
         if (ix->d_ids) cudaFree(ix->d_ids);
+        if (ix->d_wrange) cudaFree(ix->d_wrange);
         if (ix->d_w) cudaFree(ix->d_w);
         if (ix->d_term_row) cudaFree(ix->d_term_row);
         if (ix->d_tab) cudaFree(ix->d_tab);
@@ -916,6 +921,8 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
     } else if (!strcmp(name, "heavy_min")) {
         if (value < 0 || value > (1 << 28)) return fail(BM25_ERR_INVALID, "heavy_min out of range");
         ix->opt_heavy_min = (int)value;
+    } else if (!strcmp(name, "no_epoch")) {
+        ix->opt_no_epoch = value ? 1 : 0;
     } else if (!strcmp(name, "q_major")) {
         ix->opt_q_major = value ? 1 : 0;
     } else if (!strcmp(name, "generic_kernel")) {

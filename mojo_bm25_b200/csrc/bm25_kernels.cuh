@@ -85,16 +85,37 @@ constexpr int kStateInts = 8;         // ints of cursor state per (warp, query t
 __global__ void __launch_bounds__(128) k_relayout(const int32_t* __restrict__ indptr, const int32_t* __restrict__ ids_in,
                                                   const float* __restrict__ w_in, const int2* __restrict__ tptr,
                                                   int n_terms, int32_t* __restrict__ ids_out,
-                                                  float* __restrict__ w_out) {
+                                                  float* __restrict__ w_out, float2* __restrict__ wrange) {
+    __shared__ float s_mn[4], s_mx[4];
     for (int t = blockIdx.x; t < n_terms; t += gridDim.x) {
         const int s = indptr[t];
         const int n = indptr[t + 1] - s;
         const int o = tptr[t].x;
         const int padded = (n + 4) & ~3;  // >= 1 sentinel after the last posting
+        float mn = INFINITY, mx = -INFINITY;
         for (int i = threadIdx.x; i < padded; i += blockDim.x) {
+            const float wv = i < n ? w_in[s + i] : 0.f;
             ids_out[o + i] = i < n ? ids_in[s + i] : kDocNone;
-            w_out[o + i] = i < n ? w_in[s + i] : 0.f;
+            w_out[o + i] = wv;
+            if (i < n) {
+                mn = fminf(mn, wv);
+                mx = fmaxf(mx, wv);
+            }
         }
+        // wrange[t] = {smallest, largest} weight of the term ({+inf, -inf} for an empty list)
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(kFull, mn, o2));
+            mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o2));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s_mn[threadIdx.x >> 5] = mn;
+            s_mx[threadIdx.x >> 5] = mx;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            wrange[t] = make_float2(fminf(fminf(s_mn[0], s_mn[1]), fminf(s_mn[2], s_mn[3])),
+                                    fmaxf(fmaxf(s_mx[0], s_mx[1]), fmaxf(s_mx[2], s_mx[3])));
+        __syncthreads();
     }
 }
 
@@ -386,6 +407,8 @@ struct SearchArgs {
     int poison;                            // 1 (debug): fill the dynamic shared memory with 0xff before use
     int sp_major;                          // 1: CTA index = split * Q + query slot (else query slot * splits + split)
     int bulk_clear;                        // 1: clear the score tile with st.bulk (UMEMSETS) instead of vector stores
+    const float2* __restrict__ wrange;     // [n_terms] {smallest, largest} weight per term (k_relayout)
+    int no_epoch;                          // 1: zero the score tile after every tile (no exponent epochs)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -482,6 +505,8 @@ struct TopkState {
     int general;    // zero / negative scores compete: the raw-score pre-filter must not clamp at 0
     u64 theta;      // key must be > theta to compete
     float theta_f;  // cheap pre-filter on the raw score (never stricter than theta)
+    float scale;    // the tile holds score * scale (exponent epochs, a power of two; 1 when unused)
+    float floor;    // scaled tile values below floor * scale are leftovers of earlier epochs, i.e. zero
     __device__ __forceinline__ void set_theta(u64 t) {
         theta = t;
         if (t == 0ull) theta_f = -INFINITY;
@@ -622,17 +647,19 @@ struct PostingPiece {
 __device__ __forceinline__ bool tile_scan(float* scw, int S, int nd_w, uint32_t doc0, int lane, TopkState& tk) {
     bool left = false;
     const float done = tk.general ? -INFINITY : 0.f;
+    const float th = fmaxf(tk.theta_f, tk.floor) * tk.scale;  // threshold in the tile's scale
+    const float inv = 1.0f / tk.scale;                        // exact: scale is a power of two
 #pragma unroll 4
     for (int idx = lane * 4; idx < S; idx += 128) {
         const float4 v = *reinterpret_cast<const float4*>(scw + idx);
         float4 z = make_float4(done, done, done, done);
-        if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= tk.theta_f) {
+        if (fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)) >= th) {
             const float vv[4] = {v.x, v.y, v.z, v.w};
             float zz[4] = {done, done, done, done};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                if (vv[e] >= tk.theta_f && vv[e] != -INFINITY && idx + e < nd_w) {
-                    if (!tk.push(vv[e], doc0 + (uint32_t)(idx + e))) { zz[e] = vv[e]; left = true; }
+                if (vv[e] >= th && vv[e] != -INFINITY && idx + e < nd_w) {
+                    if (!tk.push(vv[e] * inv, doc0 + (uint32_t)(idx + e))) { zz[e] = vv[e]; left = true; }
                 }
             }
             z = make_float4(zz[0], zz[1], zz[2], zz[3]);
@@ -652,6 +679,10 @@ __device__ __forceinline__ void tile_clear(float* scw, int S, int lane) {
 struct CtaShared {
     int ncand, overflow;
     u64 theta;
+    // exponent epochs of this CTA's query (k_score_topk_s): scale of the first epoch, factor between
+    // epochs, scale of the last epoch, smallest possible non-zero score (all powers of two)
+    float scale0, step, top, floor;
+    float wscale[16];  // per warp: scale of the tile handed to tile_finish
     int hist[264];  // select_candidates scratch
 };
 
@@ -704,7 +735,7 @@ __device__ __forceinline__ void overflow_round(const ColdCtx& c, TopkState& tk, 
 // Returns the (possibly raised) raw-score pre-filter threshold.
 __device__ __noinline__ float tile_finish(const ColdCtx c, int base, int nd_w, int hl_n, int use_list) {
     const int lane = c.tid & 31;
-    TopkState tk{c.cand, &c.sh->ncand, &c.sh->overflow, c.cap, c.general, 0ull, 0.f};
+    TopkState tk{c.cand, &c.sh->ncand, &c.sh->overflow, c.cap, c.general, 0ull, 0.f, c.sh->wscale[c.tid >> 5], c.sh->floor};
     tk.set_theta(c.sh->theta);  // thresholds only change inside rounds, which every warp attends
     bool left = false;
     if (!use_list) {
@@ -719,7 +750,7 @@ __device__ __noinline__ float tile_finish(const ColdCtx c, int base, int nd_w, i
             if (x >= 0 && (__ffs(same) - 1) == lane) {
                 const float v = c.scw[x];
                 if (v > 0.f) {  // not yet taken by an earlier step of this loop
-                    if (tk.push(v, (uint32_t)(base + x))) c.scw[x] = 0.f;
+                    if (tk.push(v * (1.0f / tk.scale), (uint32_t)(base + x))) c.scw[x] = 0.f;
                     else left = true;
                 }
             }
@@ -741,7 +772,7 @@ __device__ __noinline__ float tile_finish(const ColdCtx c, int base, int nd_w, i
 // write the CTA's k best keys.
 __device__ __noinline__ void cta_finish(const ColdCtx c, int q_has_theta) {
     const WarpsGroup grp{c.nthreads, c.tid};
-    TopkState tk{c.cand, &c.sh->ncand, &c.sh->overflow, c.cap, c.general, 0ull, 0.f};
+    TopkState tk{c.cand, &c.sh->ncand, &c.sh->overflow, c.cap, c.general, 0ull, 0.f, 1.f, 0.f};
     tk.set_theta(c.sh->theta);
     for (;;) {
         grp.sync();
@@ -811,7 +842,9 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
         sh.overflow = 0;
         const u64 shared_theta = a.theta_q ? *reinterpret_cast<volatile u64*>(a.theta_q + q) : 0ull;
         sh.theta = shared_theta > a.theta0 ? shared_theta : a.theta0;
+        sh.floor = a.general ? -INFINITY : 1.401298464e-45f;  // this kernel keeps unscaled scores in its tiles
     }
+    if (tid < 16) sh.wscale[tid] = 1.f;
     __syncthreads();
 
     // gathered only where a rare path is entered
@@ -1084,13 +1117,12 @@ struct PieceRegs {
             w.x = __ldg(wts + idx);
         }
     }
-    __device__ __forceinline__ void add_wide(unsigned tile, int base, unsigned S, float& n0, float& n1, float& n2,
-                                             float& n3) const {
+    __device__ __forceinline__ void add_wide(unsigned tile, int base, unsigned S, float scale, float& n0, float& n1,
+                                             float& n2, float& n3) const {
         asm volatile(
             "{\n\t"
             ".reg .pred p0, p1, p2, p3;\n\t"
             ".reg .u32 s0, s1, s2, s3;\n\t"
-            ".reg .f32 v0, v1, v2, v3;\n\t"
             "sub.u32 s0, %4, %12;\n\t"
             "sub.u32 s1, %5, %12;\n\t"
             "sub.u32 s2, %6, %12;\n\t"
@@ -1107,14 +1139,14 @@ struct PieceRegs {
             "mov.f32 %1, 0f00000000;\n\t"
             "mov.f32 %2, 0f00000000;\n\t"
             "mov.f32 %3, 0f00000000;\n\t"
-            "@p0 ld.shared.f32 v0, [s0];\n\t"
-            "@p1 ld.shared.f32 v1, [s1];\n\t"
-            "@p2 ld.shared.f32 v2, [s2];\n\t"
-            "@p3 ld.shared.f32 v3, [s3];\n\t"
-            "@p0 add.f32 %0, v0, %8;\n\t"
-            "@p1 add.f32 %1, v1, %9;\n\t"
-            "@p2 add.f32 %2, v2, %10;\n\t"
-            "@p3 add.f32 %3, v3, %11;\n\t"
+            "@p0 ld.shared.f32 %0, [s0];\n\t"
+            "@p1 ld.shared.f32 %1, [s1];\n\t"
+            "@p2 ld.shared.f32 %2, [s2];\n\t"
+            "@p3 ld.shared.f32 %3, [s3];\n\t"
+            "@p0 fma.rn.f32 %0, %8, %15, %0;\n\t"
+            "@p1 fma.rn.f32 %1, %9, %15, %1;\n\t"
+            "@p2 fma.rn.f32 %2, %10, %15, %2;\n\t"
+            "@p3 fma.rn.f32 %3, %11, %15, %3;\n\t"
             "@p0 st.shared.f32 [s0], %0;\n\t"
             "@p1 st.shared.f32 [s1], %1;\n\t"
             "@p2 st.shared.f32 [s2], %2;\n\t"
@@ -1122,26 +1154,25 @@ struct PieceRegs {
             "}"
             : "=&f"(n0), "=&f"(n1), "=&f"(n2), "=&f"(n3)
             : "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w), "f"(w.x), "f"(w.y), "f"(w.z), "f"(w.w), "r"(base), "r"(S),
-              "r"(tile)
+              "r"(tile), "f"(scale)
             : "memory");
     }
-    __device__ __forceinline__ float add_narrow(unsigned tile, int base, unsigned S) const {
+    __device__ __forceinline__ float add_narrow(unsigned tile, int base, unsigned S, float scale) const {
         float n0;
         asm volatile(
             "{\n\t"
             ".reg .pred p0;\n\t"
             ".reg .u32 s0;\n\t"
-            ".reg .f32 v0;\n\t"
             "sub.u32 s0, %1, %3;\n\t"
             "setp.lt.u32 p0, s0, %4;\n\t"
             "mad.lo.u32 s0, s0, 4, %5;\n\t"
             "mov.f32 %0, 0f00000000;\n\t"
-            "@p0 ld.shared.f32 v0, [s0];\n\t"
-            "@p0 add.f32 %0, v0, %2;\n\t"
+            "@p0 ld.shared.f32 %0, [s0];\n\t"
+            "@p0 fma.rn.f32 %0, %2, %6, %0;\n\t"
             "@p0 st.shared.f32 [s0], %0;\n\t"
             "}"
             : "=&f"(n0)
-            : "r"(d.x), "f"(w.x), "r"(base), "r"(S), "r"(tile)
+            : "r"(d.x), "f"(w.x), "r"(base), "r"(S), "r"(tile), "f"(scale)
             : "memory");
         return n0;
     }
@@ -1178,6 +1209,53 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
     }
     float* scw = sc + (size_t)warp * S;
     for (int i = lane * 4; i < S; i += 128) *reinterpret_cast<float4*>(scw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 0) {
+        // ---- exponent epochs ------------------------------------------------------------------
+        // With positive weights the tile need not be zeroed after every tile: tile e of a run of E
+        // tiles accumulates weight * 2^(s0 + c*e) (fma, exact: a power of two), with c so large
+        // that whatever an earlier tile of the run left in a slot is less than half an ulp of the
+        // first weight added on top of it -- the addition returns that weight exactly, as if the
+        // slot had been zero.  The bound: every score of this query is < 2^ls (sum of the terms'
+        // largest weights) and every weight is >= 2^lw, so c = ls - lw + 26 suffices; the run
+        // length E is what the fp32 exponent range allows.  Scores are unscaled (exactly) when
+        // they leave the tile; values below floor * scale are leftovers, i.e. zero.
+        float mn = INFINITY, sum = 0.f;
+        if (lane < T) {
+            const int term = __ldg(a.queries + (int64_t)q * T + lane);
+            if (term >= 0 && term < a.n_terms) {
+                const float2 r = __ldg(a.wrange + term);
+                if (r.y >= r.x) {  // not an empty list
+                    mn = r.x;
+                    sum = r.y;
+                }
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+            sum += __shfl_xor_sync(kFull, sum, o);
+        }
+        if (lane == 0) {
+            float scale0 = 1.f, step = 1.f, top = 1.f, floor = a.general ? -INFINITY : 1.401298464e-45f;
+            if (!a.general && !a.no_epoch && mn >= 7.8886090522e-31f /* 2^-100 */ && sum >= mn &&
+                sum < 1.2676506002e30f /* 2^100 */) {
+                const int lw = (__float_as_int(mn) >> 23) - 127;         // 2^lw <= every weight
+                const int ls = (__float_as_int(sum) >> 23) - 127 + 2;    // every score < 2^ls
+                const int c = ls - lw + 26;
+                const int s0 = max(-125 - lw, -120);
+                const int E = 1 + (125 - ls - s0) / c;
+                if (E >= 2) {
+                    scale0 = __int_as_float((s0 + 127) << 23);
+                    step = __int_as_float((c + 127) << 23);
+                    top = __int_as_float((s0 + c * (E - 1) + 127) << 23);
+                    floor = __int_as_float((lw + 127) << 23);
+                }
+            }
+            sh.scale0 = scale0;
+            sh.step = step;
+            sh.top = top;
+            sh.floor = floor;
+        }
+    }
     if (tid == 0) {
         sh.ncand = 0;
         sh.overflow = 0;
@@ -1186,6 +1264,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
     }
     __syncthreads();
 
+    float scale = sh.scale0;  // scale of the current tile
     auto cold_ctx = [&]() {
         ColdCtx c;
         c.cand = a.cand_global ? a.cand_global + ((size_t)q * a.splits + sp) * a.cap : cand_smem;
@@ -1213,10 +1292,10 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
         const int j0 = chunk * a.tiles_per_chunk;
         const int j1 = min(NB, j0 + a.tiles_per_chunk);
         const bool hot_enabled = !a.general && !a.no_hot;
-        float theta_f;
+        float theta_f;  // pre-filter threshold IN THE CURRENT TILE'S SCALE
         {
             const u64 t0 = sh.theta;
-            theta_f = (t0 == 0ull) ? -INFINITY : (a.general ? key_score(t0) : fmaxf(key_score(t0), 1.401298464e-45f));
+            theta_f = (t0 == 0ull) ? -INFINITY : fmaxf(key_score(t0), sh.floor) * scale;
         }
         // ---- this lane's term -------------------------------------------------------------------
         const int32_t* tabp = nullptr;  // heavy: row of the tile table
@@ -1293,7 +1372,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
                         bool hot = false;
                         if (lane == tl) {
                             const unsigned slot = tile + 4u * (unsigned)(d0 - base);
-                            const float nw = lds_f32(slot) + __int_as_float(w0);
+                            const float nw = fmaf(__int_as_float(w0), scale, lds_f32(slot));
                             sts_f32(slot, nw);
                             hot = nw >= theta_f;
                         }
@@ -1353,11 +1432,11 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
                         __syncwarp();
                     }
                     if (narrow) {
-                        const float n0 = P.add_narrow(tile, base, uS);
+                        const float n0 = P.add_narrow(tile, base, uS, scale);
                         if (hl_n <= kHotCap) hot_add(n0 >= theta_f, P.d.x - base);  // outside the tile: n0 = 0 < theta_f
                     } else {
                         float n0, n1, n2, n3;
-                        P.add_wide(tile, base, uS, n0, n1, n2, n3);
+                        P.add_wide(tile, base, uS, scale, n0, n1, n2, n3);
                         if (hl_n <= kHotCap) {
                             if (__any_sync(kFull, fmaxf(fmaxf(n0, n1), fmaxf(n2, n3)) >= theta_f)) {
                                 hot_add(n0 >= theta_f, P.d.x - base);
@@ -1394,15 +1473,29 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
             const bool cold = a.general || (touched && hl_n != 0) || ld_volatile(&sh.overflow);
             if (!cold) {
                 if (touched) {
-                    if (a.bulk_clear) {
-                        smem_bulk_zero(tile, uS * 4u);
-                    } else {
-                        for (unsigned off = lane * 16u; off < uS * 4u; off += 512u) sts_zero16(tile + off);
+                    if (scale == sh.top) {  // last epoch of the run (always, when epochs are off): zero the tile
+                        if (a.bulk_clear) {
+                            smem_bulk_zero(tile, uS * 4u);
+                        } else {
+                            for (unsigned off = lane * 16u; off < uS * 4u; off += 512u) sts_zero16(tile + off);
+                        }
+                        const float s0 = sh.scale0;
+                        theta_f = theta_f * (1.0f / scale) * s0;
+                        scale = s0;
+                    } else {  // next epoch: what this tile left behind is below half an ulp of the next tile's weights
+                        const float up = sh.step;
+                        scale *= up;
+                        theta_f *= up;
                     }
                 }
             } else {
-                theta_f = tile_finish(cold_ctx(), base, min(S, a.n_docs - base), hl_n,
-                                      (hl_n <= kHotCap && !a.general) ? 1 : 0);
+                // returns the unscaled threshold and leaves the tile zeroed: a new run starts
+                if (lane == 0) sh.wscale[warp] = scale;
+                __syncwarp();
+                const float th = tile_finish(cold_ctx(), base, min(S, a.n_docs - base), hl_n,
+                                             (hl_n <= kHotCap && !a.general) ? 1 : 0);
+                scale = sh.scale0;
+                theta_f = fmaxf(th, sh.floor) * scale;
             }
         }
         cp_async_wait_all();  // nothing of this warp may still be in flight towards shared memory

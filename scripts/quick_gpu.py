@@ -32,7 +32,7 @@ for wl in args.workloads.split(","):
     print(f"# {wl}: docs={idx.n_docs} terms={idx.n_terms} nnz={idx.nnz} Q={q.shape[0]} T={q.shape[1]} k={k} "
           f"posting_bytes={pbytes/1e9:.3f} GB", flush=True)
     for cfg in args.configs.split(","):
-        opts = dict(tile_docs=0, splits=0, consumer_warps=0, cap=0, waves=0, no_theta_share=0, no_priming=0, no_hot=0, heavy_min=0, cand_smem=0, no_bulk_clear=0, no_query_sort=0, generic_kernel=0, q_major=0)
+        opts = dict(tile_docs=0, splits=0, consumer_warps=0, cap=0, waves=0, no_theta_share=0, no_priming=0, no_hot=0, heavy_min=0, cand_smem=0, no_bulk_clear=0, no_query_sort=0, generic_kernel=0, q_major=0, no_epoch=0)
         if cfg != "default":
             for kv in cfg.split(":"):
                 name, val = kv.split("=")

@@ -273,9 +273,10 @@ def test_every_launch_shape_gives_identical_results(engine, workload, scale, k):
         dict(no_query_sort=1), dict(no_bulk_clear=1, no_query_sort=1, splits=2),
         dict(generic_kernel=1), dict(generic_kernel=1, heavy_min=1 << 20, cap=k + 64),
         dict(q_major=1), dict(q_major=1, splits=4, cap=k + 64),
+        dict(no_epoch=1), dict(no_epoch=1, cap=k + 64, poison=1), dict(poison=1, no_bulk_clear=1),
     ]
     names = ["cap", "consumer_warps", "tile_docs", "no_hot", "no_priming", "no_theta_share", "splits", "waves",
-             "heavy_min", "poison", "no_query_sort", "no_bulk_clear", "generic_kernel", "q_major"]
+             "heavy_min", "poison", "no_query_sort", "no_bulk_clear", "generic_kernel", "q_major", "no_epoch"]
     for v in variants:
         for n in names:
             index.set_option(n, v.get(n, 0))
@@ -334,7 +335,7 @@ def test_fuzz_random_indices_and_knobs(engine):
                               ("splits", [0, 1, 2, 9]), ("cap", [0, k + 64]), ("no_hot", [0, 1]),
                               ("no_priming", [0, 1]), ("no_theta_share", [0, 1]), ("heavy_min", [0, 1, 512, 1 << 20]),
                               ("poison", [0, 1]), ("no_query_sort", [0, 1]), ("no_bulk_clear", [0, 1]),
-                              ("generic_kernel", [0, 1]), ("q_major", [0, 1])]:
+                              ("generic_kernel", [0, 1]), ("q_major", [0, 1]), ("no_epoch", [0, 1])]:
             index.set_option(name, int(rng.choice(choices)))
         _check_batch(index, indptr, indices, data, n_docs, q, k)
         index.close()

@@ -140,3 +140,52 @@ def test_large_k_uses_the_global_memory_merge_and_the_maximum_is_a_value_error()
     torch.cuda.synchronize()
     wi, ws = index.search(q, k)
     assert np.array_equal(gi.cpu().numpy(), wi) and np.array_equal(gs.cpu().numpy().view(np.uint32), ws.view(np.uint32))
+
+
+@pytest.mark.parametrize("lo_exp,hi_exp", [(-2, 2), (-12, 3), (-30, 30), (-60, 40), (-110, -90), (60, 100)])
+def test_exponent_epochs_are_exact_for_any_weight_range(lo_exp, hi_exp):
+    """k_score_topk_s does not zero its score tile after every tile: consecutive tiles accumulate
+    weight * 2^(s0 + c*e) and rely on the leftovers of earlier tiles being absorbed exactly.  The
+    spacing c and the run length are derived from the query's weight range, so sweep that range
+    (log-uniform weights over 10^lo .. 10^hi, far beyond what BM25 produces): results must be
+    bit-identical to the oracle and to the no_epoch build of the same search, with one warp
+    walking every tile of the index so that runs wrap several times."""
+    from mojo_bm25_b200 import engine
+
+    rng = np.random.default_rng(1000 + lo_exp * 7 + hi_exp)
+    n_docs, n_terms = 60_000, 40
+    cols, vals = [], []
+    indptr = np.zeros(n_terms + 1, dtype=np.int32)
+    for t in range(n_terms):
+        df = int(rng.integers(1, n_docs // (1 + t % 7)))
+        docs = np.sort(rng.choice(n_docs, size=df, replace=False)).astype(np.int32)
+        # every term spans the whole range: the smallest and the largest weight meet in one slot
+        w = (10.0 ** rng.uniform(lo_exp, hi_exp, size=df)).astype(np.float32)
+        w = np.maximum(w, np.float32(1.2e-38))
+        cols.append(docs)
+        vals.append(w)
+        indptr[t + 1] = indptr[t] + df
+    indices = np.concatenate(cols)
+    data = np.concatenate(vals)
+    q = rng.integers(0, n_terms, size=(24, 5)).astype(np.int32)
+    q[3, 2:] = -1
+    q[7, :] = q[7, 0]  # the same term five times
+    k = 50
+    index = engine.DeviceIndex(indptr, indices, data, n_docs=n_docs)
+    names = ["consumer_warps", "splits", "tile_docs", "no_epoch", "poison", "cap", "heavy_min"]
+    ref = None
+    for v in [dict(no_epoch=1), dict(), dict(consumer_warps=1, splits=1, poison=1),
+              dict(consumer_warps=1, splits=1, tile_docs=512, poison=1),
+              dict(consumer_warps=2, splits=1, tile_docs=128, cap=k + 64, poison=1),
+              dict(consumer_warps=1, splits=1, heavy_min=1 << 20, poison=1)]:
+        for n in names:
+            index.set_option(n, v.get(n, 0))
+        ids, sc = index.search(q, k)
+        if ref is None:
+            ref = (ids, sc)
+            for i in range(len(q)):
+                dense = c_oracle.scores_dense(indptr, indices, data, n_docs, q[i])
+                orc.check_topk_against_dense(ids[i], sc[i], dense, k, exact=True)
+        assert np.array_equal(ids, ref[0]), v
+        assert np.array_equal(sc.view(np.uint32), ref[1].view(np.uint32)), v
+    index.close()
