@@ -43,6 +43,9 @@ extern "C" {
 #define BM25_SMALL_K 6144 /* up to here the final merge sorts in shared memory; above, in global memory */
 #define BM25_MAX_DOCS (0x7fffffffLL - 65536) /* largest n_docs of one handle (int32 tile arithmetic) */
 
+#define BM25_WEIGHTS_FP32 0 /* int32 doc id + fp32 weight, 8 bytes per posting (the bm25s on-disk dtypes) */
+#define BM25_WEIGHTS_BF16 1 /* compressed: uint16 tile-local doc id + bf16 weight, 4 bytes per posting    */
+
 typedef struct bm25_index bm25_index; /* opaque; owns the HBM-resident CSC arrays + workspace */
 
 typedef struct bm25_index_info {
@@ -57,6 +60,8 @@ typedef struct bm25_index_info {
     int32_t all_positive; /* 1 if every weight is > 0 (enables the pruned path)*/
     int32_t was_sorted;   /* 1 if every column arrived sorted by doc id        */
     int32_t sm_count;     /* SMs of the device                                 */
+    int32_t weight_format;/* BM25_WEIGHTS_FP32 or BM25_WEIGHTS_BF16            */
+    int32_t posting_bytes;/* bytes per posting the score kernel streams: 8 or 4*/
 } bm25_index_info;
 
 /* Index loader (replaces: nothing in the reference loads the on-disk bm25s CSC index
@@ -79,6 +84,18 @@ int bm25_index_create_device(const int32_t* d_indptr, const int32_t* d_indices, 
                              int64_t n_terms, int64_t n_docs, int64_t nnz, int device,
                              int64_t doc_id_base, int borrow, bm25_index** out);
 
+/* Index compression (new; SURVEY.md 8f row 4 -- the dtypes the reference's index declares are
+ * params.index.json:1-12 "dtype": "float32", "int_dtype": "int32").  Converts the handle IN PLACE to
+ * the compressed posting format: every weight is rounded to bf16 (round to nearest even) and the
+ * score kernel for queries of <= 32 term slots streams 4-byte postings {uint16 byte offset of the
+ * document's slot inside its document tile, bf16 weight} instead of 8-byte {int32, fp32}.  From
+ * then on the handle IS the quantised index: searches and dense scores are bit-identical to the
+ * reference run on the CSC matrix with bf16-rounded weights (fp32 accumulation, query-term order).
+ * The 8-byte arrays are kept for light terms, wider queries and bm25_scores_dense.  Irreversible;
+ * requires tile_docs <= 8192.  Not thread-safe against concurrent searches of the same handle
+ * beyond the handle mutex (it waits for the device). */
+int bm25_index_compress(bm25_index* index, int weight_format);
+
 int bm25_index_destroy(bm25_index* index);
 int bm25_index_get_info(const bm25_index* index, bm25_index_info* out);
 
@@ -93,8 +110,9 @@ int bm25_index_get_info(const bm25_index* index, bm25_index_info* out);
  *   "heavy_min"      a term gets a row in the tile table when df*16 >= heavy_min * n_tiles (default 16,
  *                    i.e. one posting per document tile on average); lighter terms are walked by cursors
  *   "generic_kernel" 1: use the any-T kernel also for queries of <= 32 term slots (A/B switch)
- *   "no_query_sort" / "q_major" / "no_bulk_clear"   1: keep the batch order / query-major CTA order /
- *                    vector-store tile clear (A/B switches)
+ *   "no_query_sort" / "q_major" / "no_bulk_clear" / "no_epoch" / "no_packed"   1: keep the batch order /
+ *                    query-major CTA order / vector-store tile clear / zero the tile after every tile /
+ *                    read the 8-byte arrays of a compressed handle (A/B switches)
  *   "poison"         1 (debug): fill workspace and shared memory with 0xff before every search
  *   "no_hot" / "no_priming" / "no_theta_share"   1: disable the hot-list epilogue / the load-time
  *                    threshold priming / the per-query threshold shared between CTAs (A/B switches)
@@ -138,7 +156,8 @@ int bm25_merge_topk(const int32_t* d_ids, const float* d_scores, int n_lists, in
                     int64_t Q, int k_in, int k_out, int32_t* d_out_ids, float* d_out_scores,
                     int device, void* cuda_stream);
 
-/* Algorithmic bytes of a batch: sum_q 8*sum_t df(t) + 8*k.  Host queries. */
+/* Algorithmic bytes of a batch: sum_q 8*sum_t df(t) + 8*k (4*sum_t df(t) for a
+ * compressed handle).  Host queries. */
 int bm25_posting_bytes(const bm25_index* index, const int32_t* h_queries, int64_t Q, int64_t T,
                        int k, int64_t* out_bytes);
 

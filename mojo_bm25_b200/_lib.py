@@ -9,12 +9,13 @@ import os
 from . import build as _build
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_OOM = 0, 1, 2, 3, 4, 5
+WEIGHTS_FP32, WEIGHTS_BF16 = 0, 1
 MAX_K = 65536
 SMALL_K = 6144
 
 SYMBOLS = [
     "bm25_index_create", "bm25_index_create_device", "bm25_index_destroy", "bm25_index_get_info",
-    "bm25_index_set_option", "bm25_index_get_timing", "bm25_search", "bm25_search_host", "bm25_scores_dense",
+    "bm25_index_set_option", "bm25_index_compress", "bm25_index_get_timing", "bm25_search", "bm25_search_host", "bm25_scores_dense",
     "bm25_scores_dense_host", "bm25_merge_topk", "bm25_posting_bytes", "bm25_kernel_launches",
     "bm25_last_error", "bm25_version",
 ]
@@ -26,6 +27,7 @@ class IndexInfo(ctypes.Structure):
         ("doc_id_base", ctypes.c_int64), ("device_bytes", ctypes.c_int64),
         ("device", ctypes.c_int32), ("tile_docs", ctypes.c_int32), ("n_tiles", ctypes.c_int32),
         ("all_positive", ctypes.c_int32), ("was_sorted", ctypes.c_int32), ("sm_count", ctypes.c_int32),
+        ("weight_format", ctypes.c_int32), ("posting_bytes", ctypes.c_int32),
     ]
 
 
@@ -60,6 +62,7 @@ def load(rebuild_if_stale: bool = True):
     lib.bm25_index_destroy.argtypes = [vp]
     lib.bm25_index_get_info.argtypes = [vp, ctypes.POINTER(IndexInfo)]
     lib.bm25_index_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+    lib.bm25_index_compress.argtypes = [vp, i32]
     lib.bm25_index_get_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.bm25_search.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp]
     lib.bm25_search_host.argtypes = [vp, vp, i64, i64, i32, vp, vp]

@@ -163,11 +163,15 @@ struct bm25_index {
     int64_t n_heavy = 0, tab_bytes = 0;
     int tab_tile_docs = 0, tab_heavy_min = 0;  // what the table was built for (0 = not built)
     float* d_bounds = nullptr;  // [n_terms][kBoundLevels] per-term weight order statistics (threshold priming)
+    // compressed index (bm25_index_compress): weights rounded to bf16, 4-byte packed postings
+    int weight_format = BM25_WEIGHTS_FP32;
+    uint32_t* d_pk = nullptr;  // [nnz_padded] packed postings for pk_tile_docs documents per tile
+    int pk_tile_docs = 0;
     std::vector<int32_t> h_indptr;  // host copy for byte accounting / heavy-term selection
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
     int opt_warps = 0, opt_cap = 0, opt_waves = 0, opt_no_theta_share = 0, opt_no_priming = 0, opt_no_hot = 0, opt_heavy_min = 0, opt_cand_smem = 0;
-    int opt_poison = 0, opt_no_bulk_clear = 0, opt_no_query_sort = 0, opt_generic_kernel = 0, opt_q_major = 0, opt_no_epoch = 0;
+    int opt_poison = 0, opt_no_bulk_clear = 0, opt_no_query_sort = 0, opt_generic_kernel = 0, opt_q_major = 0, opt_no_epoch = 0, opt_no_packed = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // seg | score | merge boundaries
     bool ev_valid = false;
     // workspace: one per handle; searches on different streams are ordered through ws_done
@@ -194,7 +198,7 @@ struct bm25_index {
     }
     int n_tiles() const { return (int)std::max<int64_t>(1, (n_docs + tile_docs() - 1) / tile_docs()); }
     int64_t device_bytes() const {
-        int64_t b = n_terms * 12 + nnz_padded * 8 + tab_bytes;
+        int64_t b = n_terms * 12 + nnz_padded * 8 + tab_bytes + (d_pk ? nnz_padded * 4 : 0);
         if (d_bounds) b += n_terms * kBoundLevels * 4;
         b += ws_seg.bytes() + ws_partial.bytes() + ws_theta.bytes() + ws_cand.bytes() + ws_qkey.bytes() + ws_qperm.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
              ws_out_scores.bytes();
@@ -203,6 +207,44 @@ struct bm25_index {
 };
 
 namespace {
+
+// Per-term weight order statistics for threshold priming (k_term_bounds / k_term_bounds_exact),
+// from the handle's current weights; dropped when the index holds non-positive weights.
+int compute_bounds(bm25_index* ix) {
+    const int64_t V = ix->n_terms;
+    if (!(ix->all_positive && V > 0 && ix->nnz > 0)) {
+        if (ix->d_bounds) cudaFree(ix->d_bounds);
+        ix->d_bounds = nullptr;
+        return BM25_OK;
+    }
+    if (!ix->d_bounds && cudaMalloc(&ix->d_bounds, (size_t)V * kBoundLevels * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        ix->d_bounds = nullptr;
+        return fail(BM25_ERR_OOM, "cudaMalloc of the term-bound table failed");
+    }
+    k_term_bounds<<<(unsigned)V, 128>>>(ix->d_tptr, ix->d_w, (int)V, ix->d_bounds);
+    ++g_launches;
+    CU(cudaGetLastError());
+    // long lists: exact order statistics over all their postings
+    std::vector<int32_t> big;
+    for (int64_t t = 0; t < V; ++t)
+        if (ix->h_indptr[t + 1] - ix->h_indptr[t] > kBoundSample) big.push_back((int32_t)t);
+    if (!big.empty() && !getenv("BM25_B200_SAMPLED_BOUNDS")) {
+        int32_t* d_big = nullptr;
+        if (cudaMalloc(&d_big, big.size() * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(BM25_ERR_OOM, "cudaMalloc of the long-term list failed");
+        }
+        cudaMemcpy(d_big, big.data(), big.size() * 4, cudaMemcpyHostToDevice);
+        const int grid = (int)std::min<size_t>(big.size(), (size_t)ix->sm_count * 8);
+        k_term_bounds_exact<<<grid, 256>>>(ix->d_tptr, ix->d_w, d_big, (int)big.size(), ix->d_bounds);
+        ++g_launches;
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaFree(d_big);
+        if (e != cudaSuccess) return fail(BM25_ERR_CUDA, "k_term_bounds_exact failed: %s", cudaGetErrorString(e));
+    }
+    return BM25_OK;
+}
 
 // Builds the re-bucketed index from canonical CSC arrays resident on the device (h_indptr is the
 // host copy of the column pointers): padded posting arrays + {start, end} per term, then the
@@ -242,34 +284,7 @@ int finish_create(bm25_index* ix, const cudaDeviceProp& prop, const int32_t* d_i
         ++g_launches;
         CU(cudaGetLastError());
     }
-    if (ix->all_positive && V > 0 && ix->nnz > 0) {
-        // threshold priming table (see k_term_bounds / k_segments)
-        if (cudaMalloc(&ix->d_bounds, (size_t)V * kBoundLevels * sizeof(float)) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(BM25_ERR_OOM, "cudaMalloc of the term-bound table failed");
-        }
-        k_term_bounds<<<(unsigned)V, 128>>>(ix->d_tptr, ix->d_w, (int)V, ix->d_bounds);
-        ++g_launches;
-        CU(cudaGetLastError());
-        // long lists: exact order statistics over all their postings
-        std::vector<int32_t> big;
-        for (int64_t t = 0; t < V; ++t)
-            if (ix->h_indptr[t + 1] - ix->h_indptr[t] > kBoundSample) big.push_back((int32_t)t);
-        if (!big.empty() && !getenv("BM25_B200_SAMPLED_BOUNDS")) {
-            int32_t* d_big = nullptr;
-            if (cudaMalloc(&d_big, big.size() * 4) != cudaSuccess) {
-                cudaGetLastError();
-                return fail(BM25_ERR_OOM, "cudaMalloc of the long-term list failed");
-            }
-            cudaMemcpy(d_big, big.data(), big.size() * 4, cudaMemcpyHostToDevice);
-            const int grid = (int)std::min<size_t>(big.size(), (size_t)ix->sm_count * 8);
-            k_term_bounds_exact<<<grid, 256>>>(ix->d_tptr, ix->d_w, d_big, (int)big.size(), ix->d_bounds);
-            ++g_launches;
-            cudaError_t e = cudaDeviceSynchronize();
-            cudaFree(d_big);
-            if (e != cudaSuccess) return fail(BM25_ERR_CUDA, "k_term_bounds_exact failed: %s", cudaGetErrorString(e));
-        }
-    }
+    if (int rc = compute_bounds(ix)) return rc;
     CU(cudaDeviceSynchronize());
     return BM25_OK;
 }
@@ -323,6 +338,29 @@ int ensure_table(bm25_index* ix, int S) {
     ix->tab_bytes = entries * 4;
     ix->tab_tile_docs = S;
     ix->tab_heavy_min = hm;
+    return BM25_OK;
+}
+
+// Compressed handles: the 4-byte packed postings for S documents per tile (rebuilt with the tile size).
+int ensure_packed(bm25_index* ix, int S) {
+    if (ix->weight_format == BM25_WEIGHTS_FP32 || ix->pk_tile_docs == S) return BM25_OK;
+    if (S > kPkMaxTileDocs)
+        return fail(BM25_ERR_UNSUPPORTED, "a compressed index needs tile_docs <= %d (16-bit tile-local slots), got %d",
+                    kPkMaxTileDocs, S);
+    CU(cudaDeviceSynchronize());  // no search may still be reading the old array
+    if (!ix->d_pk && cudaMalloc(&ix->d_pk, (size_t)(ix->nnz_padded + 4) * 4) != cudaSuccess) {
+        cudaGetLastError();
+        ix->d_pk = nullptr;
+        return fail(BM25_ERR_OOM, "cudaMalloc of the packed postings (%lld) failed", (long long)ix->nnz_padded);
+    }
+    ix->pk_tile_docs = 0;
+    if (ix->nnz_padded > 0) {
+        k_pack<<<ix->sm_count * 8, 256>>>(ix->d_ids, ix->d_w, ix->nnz_padded, S, ix->d_pk);
+        ++g_launches;
+        CU(cudaGetLastError());
+        CU(cudaDeviceSynchronize());
+    }
+    ix->pk_tile_docs = S;
     return BM25_OK;
 }
 
@@ -512,12 +550,21 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
         static thread_local size_t configured[2][64] = {{0}, {0}};
         static thread_local size_t configured_s[2][64] = {{0}, {0}};
         if (a.T <= 32 && !ix->opt_generic_kernel) {  // lane-per-term specialisation
-            if (lp.warps <= BM25_LB_T / 32) {
-                if ((rc = configure_smem(k_score_topk_s<BM25_LB_T>, lp.smem, ix->smem_optin, &configured_s[0][ix->device % 64]))) return rc;
-                k_score_topk_s<BM25_LB_T><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
+            static thread_local size_t configured_p[2][64] = {{0}, {0}};
+            if (a.pk) {  // compressed handle: 4-byte packed postings
+                if (lp.warps <= BM25_LB_T / 32) {
+                    if ((rc = configure_smem(k_score_topk_s<BM25_LB_T, true>, lp.smem, ix->smem_optin, &configured_p[0][ix->device % 64]))) return rc;
+                    k_score_topk_s<BM25_LB_T, true><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
+                } else {
+                    if ((rc = configure_smem(k_score_topk_s<512, true>, lp.smem, ix->smem_optin, &configured_p[1][ix->device % 64]))) return rc;
+                    k_score_topk_s<512, true><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
+                }
+            } else if (lp.warps <= BM25_LB_T / 32) {
+                if ((rc = configure_smem(k_score_topk_s<BM25_LB_T, false>, lp.smem, ix->smem_optin, &configured_s[0][ix->device % 64]))) return rc;
+                k_score_topk_s<BM25_LB_T, false><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
             } else {
-                if ((rc = configure_smem(k_score_topk_s<512>, lp.smem, ix->smem_optin, &configured_s[1][ix->device % 64]))) return rc;
-                k_score_topk_s<512><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
+                if ((rc = configure_smem(k_score_topk_s<512, false>, lp.smem, ix->smem_optin, &configured_s[1][ix->device % 64]))) return rc;
+                k_score_topk_s<512, false><<<(unsigned)grid, lp.warps * 32, lp.smem, st>>>(a);
             }
         } else if (lp.warps <= BM25_LB_T / 32) {
             if ((rc = configure_smem(k_score_topk<BM25_LB_T>, lp.smem, ix->smem_optin, &configured[0][ix->device % 64]))) return rc;
@@ -608,6 +655,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     if (lp.cand_global && (rc = ix->ws_cand.reserve((size_t)Q * lp.splits * lp.cap))) return rc;
     if ((rc = ix->ws_seg.reserve((size_t)Q * T * (lp.seg_rows + 1)))) return rc;
     if ((rc = ensure_table(ix, lp.tile_docs))) return rc;
+    if ((rc = ensure_packed(ix, lp.tile_docs))) return rc;
     // the workspace is per handle: a search on another stream waits for the previous one
     if (ix->ws_used && ix->ws_stream != st) CU(cudaStreamWaitEvent(st, ix->ws_done, 0));
     if (ix->opt_poison) {  // debug: uninitialised workspace reads must not pass by luck
@@ -668,6 +716,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.bulk_clear = ix->opt_no_bulk_clear ? 0 : 1;
     a.wrange = ix->d_wrange;
     a.no_epoch = ix->opt_no_epoch;
+    a.pk = (ix->weight_format != BM25_WEIGHTS_FP32 && !ix->opt_no_packed) ? ix->d_pk : nullptr;
     if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
     MergeArgs m{};
@@ -848,6 +897,38 @@ int bm25_index_create_device(const int32_t* d_indptr, const int32_t* d_indices, 
     return BM25_OK;
 }
 
+int bm25_index_compress(bm25_index* ix, int weight_format) {
+    if (!ix) return fail(BM25_ERR_INVALID, "index handle is NULL");
+    if (weight_format != BM25_WEIGHTS_BF16)
+        return fail(BM25_ERR_INVALID, "weight_format must be BM25_WEIGHTS_BF16 (%d), got %d", BM25_WEIGHTS_BF16, weight_format);
+    DeviceGuard g(ix->device);
+    if (!g.ok) return fail(BM25_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    if (ix->weight_format == weight_format) return BM25_OK;
+    CU(cudaDeviceSynchronize());  // no search may still be reading the weights
+    if (ix->n_terms > 0 && ix->nnz > 0) {
+        unsigned long long* d_flags = nullptr;
+        unsigned long long h_flags[2] = {0, 0};
+        CU(cudaMalloc(&d_flags, sizeof h_flags));
+        cudaMemset(d_flags, 0, sizeof h_flags);
+        const int grid = (int)std::min<int64_t>(ix->n_terms, (int64_t)ix->sm_count * 16);
+        k_quantize<<<grid, 128>>>(ix->d_tptr, (int)ix->n_terms, ix->d_w, ix->d_wrange, d_flags);
+        ++g_launches;
+        cudaError_t e = cudaMemcpy(h_flags, d_flags, sizeof h_flags, cudaMemcpyDeviceToHost);
+        cudaFree(d_flags);
+        if (e != cudaSuccess) return fail(BM25_ERR_CUDA, "k_quantize failed: %s", cudaGetErrorString(e));
+        ix->weight_format = weight_format;  // the weights are rounded from here on, whatever follows
+        if (h_flags[1]) return fail(BM25_ERR_INVALID, "%llu weights overflow bf16", h_flags[1]);
+        if (h_flags[0]) ix->all_positive = false;  // a weight rounded to zero: every document competes
+    }
+    ix->weight_format = weight_format;
+    ix->pk_tile_docs = 0;
+    int rc = compute_bounds(ix);
+    if (rc) return rc;
+    CU(cudaDeviceSynchronize());
+    return BM25_OK;
+}
+
 int bm25_index_destroy(bm25_index* ix) {
     if (!ix) return BM25_OK;
     {
@@ -859,6 +940,7 @@ int bm25_index_destroy(bm25_index* ix) {
         if (ix->d_term_row) cudaFree(ix->d_term_row);
         if (ix->d_tab) cudaFree(ix->d_tab);
         if (ix->d_bounds) cudaFree(ix->d_bounds);
+        if (ix->d_pk) cudaFree(ix->d_pk);
         if (ix->ws_done) cudaEventDestroy(ix->ws_done);
         ix->ws_seg.release();
         ix->ws_partial.release();
@@ -893,6 +975,8 @@ int bm25_index_get_info(const bm25_index* ix, bm25_index_info* out) {
     out->all_positive = ix->all_positive ? 1 : 0;
     out->was_sorted = ix->was_sorted ? 1 : 0;
     out->sm_count = ix->sm_count;
+    out->weight_format = ix->weight_format;
+    out->posting_bytes = ix->weight_format == BM25_WEIGHTS_FP32 ? 8 : 4;
     return BM25_OK;
 }
 
@@ -923,6 +1007,8 @@ int bm25_index_set_option(bm25_index* ix, const char* name, int64_t value) {
         ix->opt_heavy_min = (int)value;
     } else if (!strcmp(name, "no_epoch")) {
         ix->opt_no_epoch = value ? 1 : 0;
+    } else if (!strcmp(name, "no_packed")) {
+        ix->opt_no_packed = value ? 1 : 0;
     } else if (!strcmp(name, "q_major")) {
         ix->opt_q_major = value ? 1 : 0;
     } else if (!strcmp(name, "generic_kernel")) {
@@ -1110,7 +1196,7 @@ int bm25_posting_bytes(const bm25_index* ix, const int32_t* h_queries, int64_t Q
         if (t >= ix->n_terms) return fail(BM25_ERR_INVALID, "token id %d out of range", t);
         postings += ix->h_indptr[t + 1] - ix->h_indptr[t];
     }
-    *out_bytes = 8 * postings + 8 * (int64_t)k * Q;
+    *out_bytes = (ix->weight_format == BM25_WEIGHTS_FP32 ? 8 : 4) * postings + 8 * (int64_t)k * Q;
     return BM25_OK;
 }
 

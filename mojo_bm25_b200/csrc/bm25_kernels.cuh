@@ -8,6 +8,7 @@
 // Kernels:
 //   k_relayout           load time: CSC postings -> padded, 16-byte aligned, sentinel-terminated posting lists
 //   k_build_table        load time: per (heavy term, document tile) first-posting table
+//   k_quantize / k_pack  compressed index: bf16-rounded weights, 4-byte packed postings (16-bit tile-local slot | bf16)
 //   k_term_bounds[_exact] load time: per-term weight order statistics (threshold priming)
 //   k_segments           per (query, term): threshold priming; cursor starts of the light terms for
 //                        every document chunk (binary search on doc id inside the term's posting list)
@@ -65,6 +66,7 @@ __host__ __device__ __forceinline__ float key_score(u64 key) { return ord_to_f32
 constexpr int kDocNone = 0x7fffffff;  // sentinel doc id: padding postings, exhausted cursors
 constexpr int kSelectMin = 256;       // candidate sets larger than this are compacted by radix select
 constexpr int kStateInts = 8;         // ints of cursor state per (warp, query term) in k_score_topk
+constexpr int kPkMaxTileDocs = 8192;  // compressed postings: the tile-local byte offset 4 * (doc mod S) is a uint16
 
 // ---------------------------------------------------------------------------------------------
 // The index in HBM ("re-bucketed into document-range tiles", built at load time):
@@ -140,6 +142,63 @@ __global__ void __launch_bounds__(256) k_build_table(const int2* __restrict__ tp
         }
     }
     tab[i] = lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Compressed index (16-bit tile-local doc ids + 16-bit weights, 4 bytes per posting).
+// k_quantize (once, bm25_index_compress): rounds every weight to bf16 (round to nearest even) IN
+//   PLACE -- from then on the handle IS the quantised index: every kernel, the order statistics and
+//   the weight ranges see the rounded weights, and results are bit-identical to the reference
+//   run on the rounded CSC matrix.  bf16 rather than fp16: widening is a 16-bit shift (exact, full
+//   rate) and the exponent range is fp32's.  Recomputes wrange; flags[0] += weights that are no
+//   longer > 0, flags[1] += weights that are no longer finite.
+// k_pack (with the tile table): pk[p] = (4 * (doc mod S)) << 16 | bf16 bits, padding -> 0xffff0000.
+//   The tile a posting belongs to is implied by its position (tile table), so the doc id needs only
+//   its offset inside the tile; stored as the byte offset of the fp32 slot.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t bf16_round_bits(uint32_t u) {  // finite input
+    return (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;
+}
+__global__ void __launch_bounds__(128) k_quantize(const int2* __restrict__ tptr, int n_terms, float* __restrict__ w,
+                                                  float2* __restrict__ wrange, unsigned long long* flags) {
+    __shared__ float s_mn[4], s_mx[4];
+    unsigned long long bad0 = 0, bad1 = 0;
+    for (int t = blockIdx.x; t < n_terms; t += gridDim.x) {
+        const int2 se = tptr[t];
+        float mn = INFINITY, mx = -INFINITY;
+        for (int i = se.x + threadIdx.x; i < se.y; i += blockDim.x) {
+            const float r = __uint_as_float(bf16_round_bits(__float_as_uint(w[i])));
+            w[i] = r;
+            if (!(r > 0.f)) ++bad0;
+            if (!(fabsf(r) <= 3.402823466e38f)) ++bad1;
+            mn = fminf(mn, r);
+            mx = fmaxf(mx, r);
+        }
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            mn = fminf(mn, __shfl_xor_sync(kFull, mn, o2));
+            mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o2));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s_mn[threadIdx.x >> 5] = mn;
+            s_mx[threadIdx.x >> 5] = mx;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            wrange[t] = make_float2(fminf(fminf(s_mn[0], s_mn[1]), fminf(s_mn[2], s_mn[3])),
+                                    fmaxf(fmaxf(s_mx[0], s_mx[1]), fmaxf(s_mx[2], s_mx[3])));
+        __syncthreads();
+    }
+    if (bad0) atomicAdd(flags + 0, bad0);
+    if (bad1) atomicAdd(flags + 1, bad1);
+}
+__global__ void __launch_bounds__(256) k_pack(const int32_t* __restrict__ ids, const float* __restrict__ w, int64_t n,
+                                              int tile_docs, uint32_t* __restrict__ pk) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int d = ids[i];
+        uint32_t v = 0xffff0000u;
+        if (d != kDocNone) v = ((uint32_t)(4 * (d % tile_docs)) << 16) | (__float_as_uint(w[i]) >> 16);
+        pk[i] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -408,6 +467,7 @@ struct SearchArgs {
     int sp_major;                          // 1: CTA index = split * Q + query slot (else query slot * splits + split)
     int bulk_clear;                        // 1: clear the score tile with st.bulk (UMEMSETS) instead of vector stores
     const float2* __restrict__ wrange;     // [n_terms] {smallest, largest} weight per term (k_relayout)
+    const uint32_t* __restrict__ pk;       // [nnz_padded] 4-byte packed postings (compressed index, k_pack), or NULL
     int no_epoch;                          // 1: zero the score tile after every tile (no exponent epochs)
 };
 
@@ -1157,6 +1217,92 @@ struct PieceRegs {
               "r"(tile), "f"(scale)
             : "memory");
     }
+    // ---- compressed index (k_pack): one 32-bit word per posting, high half = byte offset of the
+    // ---- document's slot in its tile (4 * (doc mod S)), low half = bf16 weight ------------------
+    // 128 packed postings from p0 (multiple of 4), four per lane, ONE 16-byte load (component d).
+    // The 16-byte granularity drags in up to 3 postings of other tiles on either side of the
+    // tile's range [lo, hi): validity is decided by position (w.x carries idx - lo as an int).
+    __device__ __forceinline__ void load_wide_pk(const uint32_t* __restrict__ pk, int p0, int lo, int hi, int lane) {
+        const int idx = p0 + 4 * lane;
+        w.x = __int_as_float(idx - lo);
+        if (idx < hi) d = __ldg(reinterpret_cast<const int4*>(pk + idx));
+    }
+    // up to 32 postings [lo, hi), one per lane; lanes beyond hi hold the invalid word (slot offset 0xffff)
+    __device__ __forceinline__ void load_narrow_pk(const uint32_t* __restrict__ pk, int lo, int hi, int lane) {
+        const int idx = lo + lane;
+        d.x = (int)0xffff0000u;
+        if (idx < hi) d.x = (int)__ldg(pk + idx);
+    }
+    static __device__ __forceinline__ int pk_doc(int word) { return (int)((unsigned)word >> 18); }  // tile-local doc id
+    // n = hi - lo (postings of the term in this tile)
+    __device__ __forceinline__ void add_wide_pk(unsigned tile, unsigned n, float scale, float& n0, float& n1,
+                                                float& n2, float& n3) const {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p0, p1, p2, p3;\n\t"
+            ".reg .u32 s0, s1, s2, s3, v1, v2, v3;\n\t"
+            ".reg .b32 w0, w1, w2, w3;\n\t"
+            "add.u32 v1, %8, 1;\n\t"
+            "add.u32 v2, %8, 2;\n\t"
+            "add.u32 v3, %8, 3;\n\t"
+            "setp.lt.u32 p0, %8, %9;\n\t"
+            "setp.lt.u32 p1, v1, %9;\n\t"
+            "setp.lt.u32 p2, v2, %9;\n\t"
+            "setp.lt.u32 p3, v3, %9;\n\t"
+            "shr.u32 s0, %4, 16;\n\t"
+            "shr.u32 s1, %5, 16;\n\t"
+            "shr.u32 s2, %6, 16;\n\t"
+            "shr.u32 s3, %7, 16;\n\t"
+            "add.u32 s0, s0, %10;\n\t"
+            "add.u32 s1, s1, %10;\n\t"
+            "add.u32 s2, s2, %10;\n\t"
+            "add.u32 s3, s3, %10;\n\t"
+            "shl.b32 w0, %4, 16;\n\t"
+            "shl.b32 w1, %5, 16;\n\t"
+            "shl.b32 w2, %6, 16;\n\t"
+            "shl.b32 w3, %7, 16;\n\t"
+            "mov.f32 %0, 0f00000000;\n\t"
+            "mov.f32 %1, 0f00000000;\n\t"
+            "mov.f32 %2, 0f00000000;\n\t"
+            "mov.f32 %3, 0f00000000;\n\t"
+            "@p0 ld.shared.f32 %0, [s0];\n\t"
+            "@p1 ld.shared.f32 %1, [s1];\n\t"
+            "@p2 ld.shared.f32 %2, [s2];\n\t"
+            "@p3 ld.shared.f32 %3, [s3];\n\t"
+            "@p0 fma.rn.f32 %0, w0, %11, %0;\n\t"
+            "@p1 fma.rn.f32 %1, w1, %11, %1;\n\t"
+            "@p2 fma.rn.f32 %2, w2, %11, %2;\n\t"
+            "@p3 fma.rn.f32 %3, w3, %11, %3;\n\t"
+            "@p0 st.shared.f32 [s0], %0;\n\t"
+            "@p1 st.shared.f32 [s1], %1;\n\t"
+            "@p2 st.shared.f32 [s2], %2;\n\t"
+            "@p3 st.shared.f32 [s3], %3;\n\t"
+            "}"
+            : "=&f"(n0), "=&f"(n1), "=&f"(n2), "=&f"(n3)
+            : "r"(d.x), "r"(d.y), "r"(d.z), "r"(d.w), "r"(__float_as_int(w.x)), "r"(n), "r"(tile), "f"(scale)
+            : "memory");
+    }
+    __device__ __forceinline__ float add_narrow_pk(unsigned tile, unsigned S4, float scale) const {
+        float n0;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p0;\n\t"
+            ".reg .u32 s0;\n\t"
+            ".reg .b32 w0;\n\t"
+            "shr.u32 s0, %1, 16;\n\t"
+            "setp.lt.u32 p0, s0, %2;\n\t"
+            "add.u32 s0, s0, %3;\n\t"
+            "shl.b32 w0, %1, 16;\n\t"
+            "mov.f32 %0, 0f00000000;\n\t"
+            "@p0 ld.shared.f32 %0, [s0];\n\t"
+            "@p0 fma.rn.f32 %0, w0, %4, %0;\n\t"
+            "@p0 st.shared.f32 [s0], %0;\n\t"
+            "}"
+            : "=&f"(n0)
+            : "r"(d.x), "r"(S4), "r"(tile), "f"(scale)
+            : "memory");
+        return n0;
+    }
     __device__ __forceinline__ float add_narrow(unsigned tile, int base, unsigned S, float scale) const {
         float n0;
         asm volatile(
@@ -1178,7 +1324,7 @@ struct PieceRegs {
     }
 };
 
-template <int MAXT>
+template <int MAXT, bool PK>
 __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_score_topk_s(const SearchArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int NCW = blockDim.x >> 5;
@@ -1399,7 +1545,7 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
             if (touched) {
                 // ---- accumulate: terms strictly in query order --------------------------------
                 // piece generator over the heavy terms (warp-uniform state)
-                int gp = 0, ghi = 0, gt = 0;
+                int gp = 0, ghi = 0, gt = 0, gl = 0;
                 auto next_piece = [&](bool& first, bool& narrow) -> bool {
                     if (gp + 128 < ghi) {  // only reached for wide terms
                         gp += 128;
@@ -1414,12 +1560,19 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
                     ghi = __shfl_sync(kFull, hi, gt);
                     narrow = ghi - glo <= 32;
                     gp = narrow ? glo : (glo & ~3);
+                    if (PK) gl = glo;
                     first = true;
                     return true;
                 };
                 auto fetch = [&](PieceRegs& P, bool narrow) {
-                    if (narrow) P.load_narrow(a.ids, a.w, gp, ghi, lane);
-                    else P.load_wide(a.ids, a.w, gp, ghi, lane);
+                    if (PK) {
+                        P.w.y = __int_as_float(ghi - gl);  // warp-uniform: postings of the term in this tile
+                        if (narrow) P.load_narrow_pk(a.pk, gp, ghi, lane);
+                        else P.load_wide_pk(a.pk, gp, gl, ghi, lane);
+                    } else {
+                        if (narrow) P.load_narrow(a.ids, a.w, gp, ghi, lane);
+                        else P.load_wide(a.ids, a.w, gp, ghi, lane);
+                    }
                 };
                 auto consume = [&](const PieceRegs& P, bool first, bool narrow, int tt) {
                     if (first) {  // a new term: first the light terms that precede it in the query
@@ -1431,7 +1584,23 @@ __global__ void __launch_bounds__(MAXT, MAXT == BM25_LB_T ? BM25_LB_B : 2) k_sco
                         }
                         __syncwarp();
                     }
-                    if (narrow) {
+                    if (PK) {  // compressed index: tile-local slot + bf16 weight in one word
+                        if (narrow) {
+                            const float n0 = P.add_narrow_pk(tile, uS * 4u, scale);
+                            if (hl_n <= kHotCap) hot_add(n0 >= theta_f, PieceRegs::pk_doc(P.d.x));  // invalid lanes: n0 = 0 < theta_f
+                        } else {
+                            float n0, n1, n2, n3;
+                            P.add_wide_pk(tile, (unsigned)__float_as_int(P.w.y), scale, n0, n1, n2, n3);
+                            if (hl_n <= kHotCap) {
+                                if (__any_sync(kFull, fmaxf(fmaxf(n0, n1), fmaxf(n2, n3)) >= theta_f)) {
+                                    hot_add(n0 >= theta_f, PieceRegs::pk_doc(P.d.x));
+                                    hot_add(n1 >= theta_f, PieceRegs::pk_doc(P.d.y));
+                                    hot_add(n2 >= theta_f, PieceRegs::pk_doc(P.d.z));
+                                    hot_add(n3 >= theta_f, PieceRegs::pk_doc(P.d.w));
+                                }
+                            }
+                        }
+                    } else if (narrow) {
                         const float n0 = P.add_narrow(tile, base, uS, scale);
                         if (hl_n <= kHotCap) hot_add(n0 >= theta_f, P.d.x - base);  // outside the tile: n0 = 0 < theta_f
                     } else {

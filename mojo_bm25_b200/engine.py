@@ -34,6 +34,15 @@ def _ptr(a: np.ndarray):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+def round_to_bf16(data) -> np.ndarray:
+    """fp32 array -> the fp32 values a compressed (bf16) handle stores: round to nearest even on the
+    upper 16 bits.  Host-side twin of the library's k_quantize, for callers who want to know exactly
+    which matrix a compressed index scores with."""
+    u = np.ascontiguousarray(data, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return r.astype(np.uint32).view(np.float32)
+
+
 class DeviceIndex:
     """An HBM-resident CSC BM25 index (terms = columns, documents = rows).
 
@@ -115,6 +124,15 @@ class DeviceIndex:
 
     def set_option(self, name: str, value: int):
         _lib.check(_lib.load().bm25_index_set_option(self._handle(), name.encode(), int(value)))
+
+    def compress(self, weight_format: str = "bf16") -> "DeviceIndex":
+        """Convert the handle in place to the compressed posting format (``bm25_index_compress``):
+        weights rounded to bf16, 4-byte postings {uint16 tile-local slot, bf16 weight} for the score
+        kernel.  Results are from then on those of the CSC matrix ``round_to_bf16(data)``.  Irreversible."""
+        if weight_format not in ("bf16", _lib.WEIGHTS_BF16):
+            raise ValueError("weight_format must be 'bf16'")
+        _lib.check(_lib.load().bm25_index_compress(self._handle(), _lib.WEIGHTS_BF16))
+        return self
 
     def last_timing_ms(self):
         """(segments, score+topk, merge) device ms of the last search; needs set_option("timing", 1)."""

@@ -16,6 +16,7 @@ ap.add_argument("--configs", default="default", help="comma list of option sets,
                 "(bm25_index_set_option names: tile_docs, splits, consumer_warps, cap, waves, no_theta_share)")
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--compress", action="store_true", help="bf16 / 4-byte packed postings")
 ap.add_argument("--sort-queries", action="store_true", help="order the batch by heaviest (lowest-id) term")
 args = ap.parse_args()
 
@@ -24,6 +25,8 @@ for wl in args.workloads.split(","):
     idx, q, k = synth.make_workload(wl, device="cuda", scale=args.scale)
     index = engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs)
     index.set_option("timing", 1)
+    if args.compress:
+        index.compress()
     if args.sort_queries:
         key = torch.where(q >= 0, q, torch.full_like(q, 1 << 30)).min(dim=1).values
         q = q[torch.argsort(key, stable=True)].contiguous()
@@ -32,7 +35,7 @@ for wl in args.workloads.split(","):
     print(f"# {wl}: docs={idx.n_docs} terms={idx.n_terms} nnz={idx.nnz} Q={q.shape[0]} T={q.shape[1]} k={k} "
           f"posting_bytes={pbytes/1e9:.3f} GB", flush=True)
     for cfg in args.configs.split(","):
-        opts = dict(tile_docs=0, splits=0, consumer_warps=0, cap=0, waves=0, no_theta_share=0, no_priming=0, no_hot=0, heavy_min=0, cand_smem=0, no_bulk_clear=0, no_query_sort=0, generic_kernel=0, q_major=0, no_epoch=0)
+        opts = dict(tile_docs=0, splits=0, consumer_warps=0, cap=0, waves=0, no_theta_share=0, no_priming=0, no_hot=0, heavy_min=0, cand_smem=0, no_bulk_clear=0, no_query_sort=0, generic_kernel=0, q_major=0, no_epoch=0, no_packed=0)
         if cfg != "default":
             for kv in cfg.split(":"):
                 name, val = kv.split("=")

@@ -1,0 +1,145 @@
+"""-m gpu parity tests of the compressed posting format (the reference's
+index declares "dtype": "float32", "int_dtype": "int32", animal_index_bm25/params.index.json:1-12).
+
+A compressed handle (bm25_index_compress: 4-byte postings = uint16 tile-local slot + bf16 weight) IS
+the index whose weights are rounded to bf16: every result must be bit-identical to the oracle
+(reference hot loop bm25_native.py:129-158) run on the CSC matrix ``round_to_bf16(data)``.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bm25_oracle as orc
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from mojo_bm25_b200 import engine as eng
+
+    return eng
+
+
+def _check(index, indptr, indices, data_q, n_docs, queries, k):
+    ids, sc = index.search(queries, k)
+    for i in range(len(queries)):
+        dense = c_oracle.scores_dense(indptr, indices, data_q, n_docs, queries[i])
+        orc.check_topk_against_dense(ids[i], sc[i], dense, k, exact=True)
+    return ids, sc
+
+
+def test_round_to_bf16_is_round_to_nearest_even(engine):
+    x = np.array([1.0, 1.00390625, 1.005859375, 1.01171875, 3.1415927, 1e-30, 6.5e4], np.float32)
+    r = engine.round_to_bf16(x)
+    assert np.all((r.view(np.uint32) & 0xFFFF) == 0)
+    # ties go to the even mantissa: 1 + 2^-8 -> 1.0, 1 + 3*2^-8 -> 1 + 2^-6; 1 + 3*2^-9 rounds up to 1 + 2^-7
+    assert r[1] == np.float32(1.0) and r[2] == np.float32(1.0078125) and r[3] == np.float32(1.015625)
+    assert np.all(np.abs(r - x) <= np.abs(x) * 2.0 ** -8)
+    import torch
+
+    t = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(t.view(np.uint32), r.view(np.uint32))
+
+
+@pytest.mark.parametrize("workload,scale,k", [("tiny", 1.0, 10), ("B", 0.05, 10), ("B", 0.05, 100),
+                                              ("C", 0.005, 100), ("10Mc", 0.01, 100), ("E", 0.03, 1000)])
+def test_compressed_index_equals_oracle_on_rounded_weights(engine, workload, scale, k):
+    from mojo_bm25_b200 import synth
+
+    idx, q, _ = synth.make_workload(workload, scale=scale)
+    indptr, indices, data = idx.numpy()
+    q = q.numpy()[:48]
+    k = min(k, idx.n_docs)
+    data_q = engine.round_to_bf16(data)
+    index = engine.DeviceIndex(indptr, indices, data, n_docs=idx.n_docs)
+    before = index.info
+    assert before.weight_format == 0 and before.posting_bytes == 8
+    bytes8 = index.posting_bytes(q, k)
+    index.compress("bf16")
+    info = index.info
+    assert info.weight_format == 1 and info.posting_bytes == 4
+    assert index.posting_bytes(q, k) - 8 * k * len(q) == (bytes8 - 8 * k * len(q)) // 2
+    ref = _check(index, indptr, indices, data_q, idx.n_docs, q, k)
+    # dense scores of the handle are those of the rounded matrix, bit for bit
+    dense = index.scores_dense(q[:4])
+    for i in range(4):
+        want = c_oracle.scores_dense(indptr, indices, data_q, idx.n_docs, q[i])
+        assert np.array_equal(dense[i].view(np.uint32), want.view(np.uint32))
+    # packed and unpacked kernels of the same handle, other tilings / launch shapes: identical bits
+    for opts in [dict(no_packed=1), dict(tile_docs=512, splits=3), dict(tile_docs=4096, consumer_warps=4),
+                 dict(tile_docs=8192, consumer_warps=2, splits=1), dict(no_epoch=1, poison=1), dict(heavy_min=1),
+                 dict(generic_kernel=1)]:
+        for n in ["no_packed", "tile_docs", "splits", "consumer_warps", "no_epoch", "poison", "heavy_min", "generic_kernel"]:
+            index.set_option(n, opts.get(n, 0))
+        ids, sc = index.search(q, k)
+        assert np.array_equal(ids, ref[0]), opts
+        assert np.array_equal(sc.view(np.uint32), ref[1].view(np.uint32)), opts
+    index.compress("bf16")  # idempotent
+    index.close()
+
+
+def test_compressed_matches_uncompressed_handle_of_rounded_matrix(engine):
+    """Two routes to the same numbers: compress(fp32 handle) == fp32 handle built from the rounded matrix."""
+    from mojo_bm25_b200 import synth
+
+    idx, q, _ = synth.make_workload("B", scale=0.1)
+    indptr, indices, data = idx.numpy()
+    q = q.numpy()[:200]
+    a = engine.DeviceIndex(indptr, indices, data, n_docs=idx.n_docs).compress()
+    b = engine.DeviceIndex(indptr, indices, engine.round_to_bf16(data), n_docs=idx.n_docs)
+    for k in (10, 100):
+        ia, sa = a.search(q, k)
+        ib, sb = b.search(q, k)
+        assert np.array_equal(ia, ib) and np.array_equal(sa.view(np.uint32), sb.view(np.uint32))
+    a.close()
+    b.close()
+
+
+def test_compressed_tile_limit_and_bad_format(engine):
+    from mojo_bm25_b200 import synth
+
+    idx, q, k = synth.make_workload("tiny")
+    indptr, indices, data = idx.numpy()
+    index = engine.DeviceIndex(indptr, indices, data, n_docs=idx.n_docs)
+    with pytest.raises(ValueError):
+        index.compress("fp8")
+    index.compress()
+    bidx, bq, _ = synth.make_workload("B", scale=0.05)
+    big = engine.DeviceIndex(*bidx.numpy(), n_docs=bidx.n_docs).compress()
+    big.set_option("tile_docs", 16384)  # tile-local slots are 16-bit byte offsets: 8192 documents at most
+    with pytest.raises(Exception):
+        big.search(bq.numpy()[:2], 5)
+    big.set_option("tile_docs", 0)
+    big.search(bq.numpy()[:2], 5)
+    big.close()
+    index.close()
+
+
+def test_compressed_fuzz(engine):
+    """Seeded fuzz over index shapes, ragged queries and launch knobs, compressed handles only."""
+    rng = np.random.default_rng(int(os.environ.get("BM25_FUZZ_SEED", "20260118")) + 7)
+    for trial in range(30):
+        n_docs = int(rng.choice([1, 2, 37, 500, 2049, 7000, 30000]))
+        n_terms = int(rng.integers(1, 40))
+        cols, ptr = [], [0]
+        for t in range(n_terms):
+            dens = [0.0, 0.002, 0.05, 0.9][rng.integers(0, 4)]
+            rows = np.flatnonzero(rng.random(n_docs) < dens).astype(np.int32)
+            cols.append(rows)
+            ptr.append(ptr[-1] + len(rows))
+        indices = np.concatenate(cols) if ptr[-1] else np.zeros(0, np.int32)
+        data = (0.01 + rng.random(ptr[-1]) * rng.choice([1.0, 8.0])).astype(np.float32)
+        indptr = np.array(ptr, np.int32)
+        index = engine.DeviceIndex(indptr, indices, data, n_docs=n_docs).compress()
+        data_q = engine.round_to_bf16(data)
+        q = rng.integers(-1, n_terms, size=(int(rng.integers(1, 9)), int(rng.integers(1, 12)))).astype(np.int32)
+        k = int(min(n_docs, rng.choice([1, 3, 10, 100, 1000])))
+        for name, choices in [("tile_docs", [0, 128, 512, 4096]), ("consumer_warps", [0, 1, 3, 8, 16]),
+                              ("splits", [0, 1, 2, 9]), ("cap", [0, k + 64]), ("no_hot", [0, 1]),
+                              ("heavy_min", [0, 1, 512, 1 << 20]), ("poison", [0, 1]), ("no_epoch", [0, 1])]:
+            index.set_option(name, int(rng.choice(choices)))
+        _check(index, indptr, indices, data_q, n_docs, q, k)
+        index.close()
