@@ -27,6 +27,7 @@ class BM25:
         self.vocab_dict = {}
         self.corpus = None
         self.scores = None  # {"data", "indices", "indptr", "num_docs"} like bm25s
+        self.nonoccurrence_array = None  # fp32 [V] for method bm25l / bm25+ (bm25s' attribute of the same name)
         self._index: Optional[DeviceIndex] = None
 
     # --- index side ---------------------------------------------------------------------------
@@ -37,6 +38,7 @@ class BM25:
         self = cls(k1=p.get("k1", 1.5), b=p.get("b", 0.75), delta=p.get("delta", 0.5),
                    method=p.get("method", "lucene"), device=device)
         self._attach(disk.indptr, disk.indices, disk.data, disk.num_docs, disk.vocab, disk.corpus)
+        self.nonoccurrence_array = disk.nonoccurrence
         return self
 
     @classmethod
@@ -72,10 +74,12 @@ class BM25:
         if n_terms is None:
             n_terms = len(vocab) if vocab is not None else (max((max(d) for d in docs if d), default=-1) + 1)
         flat, doc_ptr = index_build.flatten_corpus(docs)
-        variant = "bm25py" if self.method == "bm25py" else "lucene"
+        variant = self.method if self.method in index_build.VARIANTS else "lucene"
         indptr, indices, data, _ = index_build.build_csc(flat, doc_ptr, n_terms, k1=self.k1, b=self.b, variant=variant,
-                                                         device=f"cuda:{self.device}")
+                                                         device=f"cuda:{self.device}", delta=self.delta)
         torch.cuda.synchronize(self.device)
+        df = (indptr[1:] - indptr[:-1]).cpu().numpy()
+        self.nonoccurrence_array = index_build.nonoccurrence(df, len(docs), variant, k1=self.k1, delta=self.delta)
         self.vocab_dict = dict(vocab) if vocab is not None else {}
         self.corpus = None
         self.scores = {"data": data.cpu().numpy(), "indices": indices.cpu().numpy(), "indptr": indptr.cpu().numpy(),
@@ -90,7 +94,8 @@ class BM25:
         s = self.scores
         index_io.save_index(save_dir, s["indptr"], s["indices"], s["data"], self.vocab_dict, s["num_docs"],
                             k1=self.k1, b=self.b, delta=self.delta, method=self.method,
-                            corpus=corpus if corpus is not None else self.corpus)
+                            corpus=corpus if corpus is not None else self.corpus,
+                            nonoccurrence=self.nonoccurrence_array)
 
     # --- query side ---------------------------------------------------------------------------
     def get_tokens_ids(self, tokens: Iterable[str]) -> List[int]:
@@ -134,6 +139,14 @@ class BM25:
         if q.size and int(q.max(initial=-1)) >= self._index.n_terms:
             raise ValueError("query token id is outside the index vocabulary")
         ids, scores = self._index.search(q, int(k))
+        if self.nonoccurrence_array is not None:
+            # bm25l / bm25+: every document also gets the non-occurrence score of every query token
+            # (bm25s adds ``nonoccurrence_array[query_tokens_ids].sum()`` to the whole score vector:
+            # a per-query constant, so the ranking found on the device is unchanged)
+            for i in range(q.shape[0]):
+                row = q[i][q[i] >= 0]
+                if row.size:
+                    scores[i] += self.nonoccurrence_array[row].sum()
         docs = ids
         corpus = corpus if corpus is not None else self.corpus
         if corpus is not None:

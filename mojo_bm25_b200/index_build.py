@@ -11,11 +11,20 @@ The sort / run-length / histogram steps are torch (CUB) calls -- this is index c
 the query hot path; all arithmetic is IEEE float64/float32 elementwise in the order the reference
 uses, so the weights are bit-identical to the CPU formulas (tests/test_index_build.py).
 
-Variants:
-  * ``"bm25py"``  bm25.py:105,112-121:  idf * tf*(k1+1) / (tf + k1*(1-b+b*dl/avgdl)),
-                  idf = ln((N-df+.5)/(df+.5)+1)
-  * ``"lucene"``  bm25s 0.2.12 method="lucene" (the bundled animal_index_bm25 weights):
-                  idf * tf / (tf + k1*(1-b+b*dl/avgdl)), same idf
+Variants (norm = k1*(1-b+b*dl/avgdl)):
+  * ``"bm25py"``  bm25.py:105,112-121:  idf * tf*(k1+1) / (tf + norm),  idf = ln((N-df+.5)/(df+.5)+1)
+  * ``"lucene"``  bm25s 0.2.12 method="lucene" (the bundled animal_index_bm25 weights, pinned):
+                  idf * tf / (tf + norm), same idf
+  * the other scorers bm25s' ``method`` parameter names (animal_index_bm25/params.index.json:4-5),
+    after the formulas bm25s publishes -- bm25s itself is not in /root/reference, so nothing pins
+    their last bit ("parity unpinned"):
+      ``"robertson"``  tf/(tf+norm),                         idf = ln(max(1, (N-df+.5)/(df+.5)))
+      ``"atire"``      tf*(k1+1)/(tf+norm),                  idf = ln(N/df)
+      ``"bm25l"``      (k1+1)*(c+delta)/(k1+c+delta), c = tf/(1-b+b*dl/avgdl),  idf = ln((N+1)/(df+.5))
+      ``"bm25+"``      tf*(k1+1)/(tf+norm) + delta,          idf = ln((N+1)/df)
+    bm25l and bm25+ give a document WITHOUT the term a non-zero contribution idf*tfc(tf=0); bm25s
+    keeps the matrix sparse by storing weight - that contribution and a per-term
+    ``nonoccurrence_array`` that is added back per query (``nonoccurrence(...)`` below).
 """
 from __future__ import annotations
 
@@ -44,8 +53,41 @@ def _idf_host(df: np.ndarray, n_docs: int) -> np.ndarray:
     return np.log((n_docs - dfd + 0.5) / (dfd + 0.5) + 1.0)
 
 
+VARIANTS = ("lucene", "bm25py", "robertson", "atire", "bm25l", "bm25+")
+
+
+def _idf_variant_host(df: np.ndarray, n_docs: int, variant: str) -> np.ndarray:
+    """Per-term idf in float64 (math.log term by term, like bm25s' scalar idf functions)."""
+    if variant in ("lucene", "bm25py"):
+        return _idf_host(df, n_docs)
+    out = np.zeros(df.shape[0], dtype=np.float64)
+    for i, d in enumerate(df):
+        d = int(d)
+        if d == 0:
+            continue  # a term without postings has no weight to scale
+        if variant == "robertson":
+            out[i] = math.log(max(1.0, (n_docs - d + 0.5) / (d + 0.5)))
+        elif variant == "atire":
+            out[i] = math.log(n_docs / d)
+        elif variant == "bm25l":
+            out[i] = math.log((n_docs + 1) / (d + 0.5))
+        else:  # bm25+
+            out[i] = math.log((n_docs + 1) / d)
+    return out
+
+
+def nonoccurrence(df, n_docs: int, variant: str, k1: float = 1.5, delta: float = 0.5) -> Optional[np.ndarray]:
+    """Per-term score of a document that does NOT contain the term: float32 [V] for bm25l
+    (idf*(k1+1)*delta/(k1+delta)) and bm25+ (idf*delta), None for the other variants (zero)."""
+    if variant not in ("bm25l", "bm25+"):
+        return None
+    idf = _idf_variant_host(np.asarray(df), n_docs, variant)
+    tfc0 = (k1 + 1) * delta / (k1 + delta) if variant == "bm25l" else delta
+    return (idf * tfc0).astype(np.float32)
+
+
 def build_csc(token_ids, doc_ptr, n_terms: Optional[int] = None, k1: float = 1.5, b: float = 0.75,
-              variant: str = "lucene", device: str = "cuda"):
+              variant: str = "lucene", device: str = "cuda", delta: float = 0.5):
     """Build the CSC weight matrix on ``device``.
 
     token_ids : int32 [n_tokens]  term id of every token occurrence, documents concatenated
@@ -53,8 +95,8 @@ def build_csc(token_ids, doc_ptr, n_terms: Optional[int] = None, k1: float = 1.5
     Returns ``(indptr int32 [V+1], indices int32 [nnz], data float32 [nnz], doc_len int32 [N])``
     as tensors on ``device`` (``nnz`` < 2**31: shard larger corpora by document range).
     """
-    if variant not in ("lucene", "bm25py"):
-        raise ValueError("variant must be 'lucene' or 'bm25py'")
+    if variant not in VARIANTS:
+        raise ValueError(f"variant must be one of {VARIANTS}")
     dev = torch.device(device)
     tok = torch.as_tensor(token_ids).to(dev, dtype=torch.int64)
     ptr = torch.as_tensor(doc_ptr).to(dev, dtype=torch.int64)
@@ -82,7 +124,7 @@ def build_csc(token_ids, doc_ptr, n_terms: Optional[int] = None, k1: float = 1.5
     indptr = torch.zeros(n_terms + 1, dtype=torch.int64, device=dev)
     torch.cumsum(df, 0, out=indptr[1:])
     # per-term idf (host, float64, then float32 like bm25.py:118), per-document length norm (float64)
-    idf32 = torch.from_numpy(_idf_host(df.cpu().numpy(), n_docs).astype(np.float32)).to(dev)
+    idf32 = torch.from_numpy(_idf_variant_host(df.cpu().numpy(), n_docs, variant).astype(np.float32)).to(dev)
     dl = doc_len.to(torch.float32)  # bm25.py keeps doc_len as float32 for the norm
     avgdl = float(np.mean(doc_len.cpu().numpy())) if n_docs else 0.0
     if avgdl == 0:
@@ -94,6 +136,15 @@ def build_csc(token_ids, doc_ptr, n_terms: Optional[int] = None, k1: float = 1.5
         # (tf32 * (k1+1)) in float32, then float64 for the division and the idf product (numpy promotion)
         num = (tf32 * np.float32(k1 + 1)).to(torch.float64)
         w = num / (tf32.to(torch.float64) + norm[doc]) * idf32[term].to(torch.float64)
-    else:
+    elif variant in ("lucene", "robertson"):
         w = idf32[term].to(torch.float64) * tf32.to(torch.float64) / (tf32.to(torch.float64) + norm[doc])
+    else:
+        tf64, idf64 = tf32.to(torch.float64), idf32[term].to(torch.float64)
+        if variant == "atire":
+            w = idf64 * (tf64 * (k1 + 1)) / (tf64 + norm[doc])
+        elif variant == "bm25l":  # stored minus the non-occurrence score idf * tfc(tf = 0)
+            c = tf64 / (norm[doc] / k1)
+            w = idf64 * ((k1 + 1) * (c + delta) / (k1 + c + delta) - (k1 + 1) * delta / (k1 + delta))
+        else:  # bm25+: (tfc + delta) - delta
+            w = idf64 * ((tf64 * (k1 + 1)) / (tf64 + norm[doc]))
     return indptr.to(torch.int32), doc.to(torch.int32), w.to(torch.float32), doc_len.to(torch.int32)

@@ -21,6 +21,7 @@ import numpy as np
 
 DATA, INDICES, INDPTR = "data.csc.index.npy", "indices.csc.index.npy", "indptr.csc.index.npy"
 VOCAB, PARAMS = "vocab.index.json", "params.index.json"
+NONOCC = "nonoccurrence_array.index.npy"  # bm25s writes it for method bm25l / bm25+ only
 CORPUS, CORPUS_INDEX = "corpus.jsonl", "corpus.mmindex.json"
 
 
@@ -33,6 +34,7 @@ class DiskIndex:
     params: dict
     corpus: Optional[object] = None  # JsonlCorpus (offset-indexed) or a list
     corpus_offsets: List[int] = field(default_factory=list)
+    nonoccurrence: Optional[np.ndarray] = None  # fp32 [V] per-term score of documents without the term
 
     @property
     def num_docs(self) -> int:
@@ -130,12 +132,17 @@ def load_index(path: str, load_corpus: bool = False, mmap: bool = False) -> Disk
                 for line in f:
                     if line.strip():
                         corpus.append(json.loads(line))
-    return DiskIndex(indptr, indices, data, vocab, params, corpus, offsets)
+    nonocc = None
+    if os.path.exists(os.path.join(path, NONOCC)):
+        nonocc = np.ascontiguousarray(np.load(os.path.join(path, NONOCC)), dtype=np.float32)
+        if nonocc.shape != (indptr.shape[0] - 1,):
+            raise ValueError("nonoccurrence_array must hold one value per term")
+    return DiskIndex(indptr, indices, data, vocab, params, corpus, offsets, nonocc)
 
 
 def save_index(path: str, indptr, indices, data, vocab: Dict[str, int], num_docs: int, k1: float = 1.5,
                b: float = 0.75, delta: float = 0.5, method: str = "lucene", corpus: Optional[List] = None,
-               version: str = "0.2.12") -> None:
+               version: str = "0.2.12", nonoccurrence=None) -> None:
     os.makedirs(path, exist_ok=True)
     indptr = np.ascontiguousarray(indptr, dtype="<i4")
     indices = np.ascontiguousarray(indices, dtype="<i4")
@@ -144,6 +151,8 @@ def save_index(path: str, indptr, indices, data, vocab: Dict[str, int], num_docs
     np.save(os.path.join(path, DATA), data, allow_pickle=False)
     np.save(os.path.join(path, INDICES), indices, allow_pickle=False)
     np.save(os.path.join(path, INDPTR), indptr, allow_pickle=False)
+    if nonoccurrence is not None:
+        np.save(os.path.join(path, NONOCC), np.ascontiguousarray(nonoccurrence, dtype="<f4"), allow_pickle=False)
     params = dict(k1=k1, b=b, delta=delta, method=method, idf_method=method, dtype="float32", int_dtype="int32",
                   num_docs=int(num_docs), version=version, backend="numpy")
     with open(os.path.join(path, PARAMS), "w") as f:

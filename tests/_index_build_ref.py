@@ -6,6 +6,26 @@ import numpy as np
 from mojo_bm25_b200.index_build import _idf_host
 
 
+def bm25s_method_weights_float64(tf, df, n_docs, dl, avgdl, method, k1=1.5, b=0.75, delta=0.5):
+    """Scalar float64 restatement of the published bm25s scorers (score of one posting and the
+    non-occurrence score of its term); an independent route to the builder's numbers."""
+    import math
+
+    norm = 1 - b + b * dl / avgdl
+    if method == "robertson":
+        return math.log(max(1.0, (n_docs - df + 0.5) / (df + 0.5))) * tf / (k1 * norm + tf), 0.0
+    if method == "atire":
+        return math.log(n_docs / df) * tf * (k1 + 1) / (tf + k1 * norm), 0.0
+    if method == "bm25l":
+        idf, c = math.log((n_docs + 1) / (df + 0.5)), tf / norm
+        non = idf * (k1 + 1) * delta / (k1 + delta)
+        return idf * (k1 + 1) * (c + delta) / (k1 + c + delta) - non, non
+    if method == "bm25+":
+        idf = math.log((n_docs + 1) / df)
+        return idf * (tf * (k1 + 1) / (k1 * norm + tf) + delta) - idf * delta, idf * delta
+    raise ValueError(method)
+
+
 def build_csc_reference_numpy(token_ids, doc_ptr, n_terms: int, k1: float = 1.5, b: float = 0.75,
                               variant: str = "lucene"):
     """The same computation in numpy on the host (what mojo_bm25_b200.bm25.BM25.fit does for the

@@ -171,3 +171,64 @@ def test_builder_on_gpu_and_bm25s_shaped_index_roundtrip(tmp_path):
     r2.save(str(tmp_path / "idx"))
     b = BM25.load(str(tmp_path / "idx")).retrieve([["lazy", "fox"]], k=3)
     assert np.array_equal(a.documents, b.documents) and np.array_equal(a.scores, b.scores)
+
+
+@pytest.mark.parametrize("method", ["robertson", "atire", "bm25l", "bm25+"])
+def test_bm25s_scorer_variants_follow_the_published_formulas(method):
+    """SURVEY.md section 8f row 4 (bm25l / bm25+ and the other ``method`` values of
+    params.index.json:4-5).  bm25s is not in /root/reference, so these are checked against an
+    independent scalar float64 restatement of the published formulas -- parity with bm25s itself
+    is unpinned."""
+    from _index_build_ref import bm25s_method_weights_float64
+
+    rng = np.random.default_rng(3)
+    corpus = _random_corpus(rng, 120, 40, 9)
+    flat, ptr = index_build.flatten_corpus(corpus)
+    indptr, indices, data, dl = (x.numpy() for x in index_build.build_csc(flat, ptr, 40, variant=method, device="cpu",
+                                                                          k1=1.2, b=0.6, delta=0.7))
+    df = np.diff(indptr)
+    non = index_build.nonoccurrence(df, 120, method, k1=1.2, delta=0.7)
+    assert (non is not None) == (method in ("bm25l", "bm25+"))
+    avgdl = float(np.mean(dl))
+    assert np.all(data >= 0) and (method == "robertson" or np.all(data > 0))
+    for t in range(40):
+        for p in range(indptr[t], indptr[t + 1]):
+            d = indices[p]
+            tf = corpus[d].count(t)
+            w, n0 = bm25s_method_weights_float64(tf, int(df[t]), 120, float(dl[d]), avgdl, method, k1=1.2, b=0.6, delta=0.7)
+            assert abs(data[p] - w) <= 4e-7 * max(abs(w), 1e-3), (t, d)
+            if non is not None:
+                assert abs(non[t] - n0) <= 4e-7 * abs(n0)
+
+
+@pytest.mark.gpu
+def test_bm25l_and_bm25plus_retrieve_adds_nonoccurrence_scores(tmp_path):
+    """Scores of a bm25l / bm25+ index = sparse part (device top-k) + the per-query non-occurrence
+    constant; ranking equals the ranking of the full dense score vector; save/load keeps the array."""
+    from mojo_bm25_b200.bm25s_api import BM25
+
+    rng = np.random.default_rng(21)
+    corpus = _random_corpus(rng, 2000, 300, 20)
+    for method in ("bm25l", "bm25+"):
+        r = BM25(method=method, delta=0.5)
+        r.index(corpus, n_terms=300)
+        assert r.nonoccurrence_array is not None and r.nonoccurrence_array.shape == (300,)
+        q = rng.integers(0, 300, size=(8, 4)).astype(np.int32)
+        q[2, 2:] = -1
+        res = r.retrieve(q, k=10)
+        s = r.scores
+        for i in range(len(q)):
+            toks = q[i][q[i] >= 0]
+            dense = np.zeros(2000, np.float32)
+            for t in toks:  # sparse part in query order, like the hot loop
+                sl = slice(s["indptr"][t], s["indptr"][t + 1])
+                dense[s["indices"][sl]] += s["data"][sl]
+            dense = dense + r.nonoccurrence_array[toks].sum()
+            order = np.lexsort((np.arange(2000), -dense))[:10]
+            assert np.array_equal(res.scores[i], dense[order])           # the 10 best full scores ...
+            assert np.array_equal(dense[res.documents[i]], res.scores[i])  # ... and documents that have them
+        r.save(str(tmp_path / method))
+        again = BM25.load(str(tmp_path / method))
+        assert again.method == method and np.array_equal(again.nonoccurrence_array, r.nonoccurrence_array)
+        res2 = again.retrieve(q, k=10)
+        assert np.array_equal(res2.documents, res.documents) and np.array_equal(res2.scores, res.scores)
