@@ -394,8 +394,10 @@ def measure_single(ctx, index, q, k, steps, warmup, want_e2e=True):
     return rec
 
 
-def sub_workload(ctx, name, k=0, steps=10, warmup=3, index=None, idx=None):
-    """A sub-record: another named workload (or another k on an existing index), same measurement."""
+def sub_workload(ctx, name, k=0, steps=10, warmup=3, index=None, idx=None, compress=False):
+    """A sub-record: another named workload (or another k on an existing index), same measurement.
+    compress: the handle is converted to the 4-byte posting format (bf16 weights) first; its roofline
+    is then counted at 4 bytes per posting -- reported beside, never instead of, the int32/fp32 record."""
     from mojo_bm25_b200 import engine, synth
 
     args = ctx.args
@@ -403,6 +405,8 @@ def sub_workload(ctx, name, k=0, steps=10, warmup=3, index=None, idx=None):
     if own:
         idx, q, k0 = synth.make_workload(name, device=str(ctx.dev), index_seed=0, query_seed=1 + ctx.rank, scale=args.scale)
         index = engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs)
+        if compress:
+            index.compress("bf16")
     else:
         cfg = synth.WORKLOADS[name]
         q = synth.synth_queries(idx.n_terms, cfg["n_queries"], cfg["n_query_terms"], r0=cfg.get("r0", 8),
@@ -416,6 +420,11 @@ def sub_workload(ctx, name, k=0, steps=10, warmup=3, index=None, idx=None):
     rec["config"] = workload_config(args, name, idx.n_docs, idx.n_terms, idx.nnz, int(q.shape[0]), int(q.shape[1]), k,
                                     synth.WORKLOADS[name].get("r0", 8), mode, ctx.world, 1)
     rec["metric"], rec["unit"] = METRIC, UNIT
+    if compress:
+        rec["posting_format"] = ("compressed: uint16 tile-local doc id + bf16 weight = 4 B per posting (weights rounded to "
+                                 "bf16; results bit-identical to the reference on the rounded matrix, tests/test_gpu_compressed.py)")
+        rec["roofline"]["bytes_per_posting"] = 4
+        rec["roofline"]["frac_if_counted_at_8_bytes_per_posting"] = 2 * rec["roofline"]["frac"]
     if own:
         index.close()
     return rec
@@ -596,6 +605,8 @@ def run_ours(args):
             sub_steps = max(5, min(args.steps, 10))
             if args.workload != "10M":
                 subs["w10M"] = sub_workload(ctx, "10M", steps=sub_steps)
+                torch.cuda.empty_cache()
+                subs["w10M_bf16"] = sub_workload(ctx, "10M", steps=sub_steps, compress=True)
             torch.cuda.empty_cache()
             if world == 1 and args.workload != "C":
                 subs["wC"] = sub_workload(ctx, "C", steps=5)
