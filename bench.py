@@ -357,12 +357,16 @@ def e2e_host(ctx, index, qn, k, steps, units):
     for _ in range(2):
         index.search(qn, k)
     ctx.barrier()
-    t0 = time.perf_counter()
+    total = 0.0
     for _ in range(steps):
+        # the L2 flush is measurement apparatus: it has finished before the step's clock starts; the
+        # call itself returns only after the results are in host memory (it synchronises its stream)
         ctx.flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         hid, hsc = index.search(qn, k)
-    torch.cuda.synchronize()
-    e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
+        total += time.perf_counter() - t0
+    e2e_s = ctx.max_over_ranks(total)
     return {"value": units / (e2e_s / steps), "unit": UNIT, "h2d_bytes_per_step": int(qn.nbytes),
             "d2h_bytes_per_step": int(hid.nbytes + hsc.nbytes), "api": "bm25_search_host via DeviceIndex.search"}
 

@@ -678,7 +678,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
         const int P = next_pow2(Q);
         if ((rc = ix->ws_qperm.reserve((size_t)Q))) return rc;
         if (P > 4096 && (rc = ix->ws_qkey.reserve((size_t)P))) return rc;
-        k_query_order<<<1, 1024, P <= 4096 ? (size_t)P * 8 : 0, st>>>(ix->d_tptr, d_queries, (int)Q, (int)T,
+        k_query_order<<<1, 1024, P <= 4096 ? (size_t)std::max(P, 1024) * 8 : 0, st>>>(ix->d_tptr, d_queries, (int)Q, (int)T,
                                                                       (int)ix->n_terms, P, ix->ws_qkey.p, ix->ws_qperm.p);
         ++g_launches;
         CU(cudaGetLastError());
@@ -1070,19 +1070,20 @@ int bm25_search_host(bm25_index* ix, const int32_t* h_queries, int64_t Q, int64_
     if (!g.ok) return fail(BM25_ERR_CUDA, "cudaSetDevice(%d) failed", ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     const size_t nq = (size_t)Q * T, no = (size_t)Q * k;
-    if ((rc = ix->pin_queries.reserve(nq)) || (rc = ix->pin_out_ids.reserve(no)) ||
-        (rc = ix->pin_out_scores.reserve(no)) || (rc = ix->ws_queries.reserve(nq)) ||
-        (rc = ix->ws_out_ids.reserve(no)) || (rc = ix->ws_out_scores.reserve(no)))
+    // ids and scores share one device buffer and one pinned buffer: [no] int32 ids | [no] fp32 scores,
+    // so the results come back in ONE device-to-host copy
+    if ((rc = ix->pin_queries.reserve(nq)) || (rc = ix->pin_out_ids.reserve(2 * no)) ||
+        (rc = ix->ws_queries.reserve(nq)) || (rc = ix->ws_out_ids.reserve(2 * no)))
         return rc;
     cudaStream_t st = ix->own_stream;
     memcpy(ix->pin_queries.p, h_queries, nq * 4);
     CU(cudaMemcpyAsync(ix->ws_queries.p, ix->pin_queries.p, nq * 4, cudaMemcpyHostToDevice, st));
-    if ((rc = search_locked(ix, ix->ws_queries.p, Q, T, k, ix->ws_out_ids.p, ix->ws_out_scores.p, st))) return rc;
-    CU(cudaMemcpyAsync(ix->pin_out_ids.p, ix->ws_out_ids.p, no * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(ix->pin_out_scores.p, ix->ws_out_scores.p, no * 4, cudaMemcpyDeviceToHost, st));
+    float* d_scores = reinterpret_cast<float*>(ix->ws_out_ids.p + no);
+    if ((rc = search_locked(ix, ix->ws_queries.p, Q, T, k, ix->ws_out_ids.p, d_scores, st))) return rc;
+    CU(cudaMemcpyAsync(ix->pin_out_ids.p, ix->ws_out_ids.p, 2 * no * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     memcpy(h_out_ids, ix->pin_out_ids.p, no * 4);
-    memcpy(h_out_scores, ix->pin_out_scores.p, no * 4);
+    memcpy(h_out_scores, ix->pin_out_ids.p + no, no * 4);
     return BM25_OK;
 }
 

@@ -428,6 +428,30 @@ __global__ void __launch_bounds__(1024) k_query_order(const int2* __restrict__ t
         keys[q] = key;
     }
     __syncthreads();
+    if (P <= 1024) {
+        // one key per thread (threads beyond P hold the largest key): compare distances below 32 are
+        // warp shuffles, only the 15 steps with distance >= 32 go through shared memory and a barrier
+        u64 x = tid < P ? keys[tid] : ~0ull;
+        __syncthreads();
+        for (int size = 2; size <= 1024; size <<= 1) {
+            const bool asc = (tid & size) == 0;
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                u64 y;
+                if (stride >= 32) {
+                    keys[tid] = x;
+                    __syncthreads();
+                    y = keys[tid ^ stride];
+                    __syncthreads();
+                } else {
+                    y = __shfl_xor_sync(kFull, x, stride);
+                }
+                const bool lower = (tid & stride) == 0;
+                x = (lower == asc) ? (x < y ? x : y) : (x < y ? y : x);
+            }
+        }
+        if (tid < Q) perm[tid] = (int32_t)(uint32_t)x;
+        return;
+    }
     for (int size = 2; size <= P; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int i = tid; i < (P >> 1); i += 1024) {

@@ -147,8 +147,8 @@ class DeviceIndex:
         if q.ndim != 2:
             raise ValueError("queries must be 2-D [Q, T]")
         qn, tn = q.shape
-        ids = np.zeros((qn, int(k)), np.int32)
-        scores = np.zeros((qn, int(k)), np.float32)
+        ids = np.empty((qn, int(k)), np.int32)  # fully overwritten by the library
+        scores = np.empty((qn, int(k)), np.float32)
         if tn == 0:
             q = np.full((qn, 1), -1, np.int32)
             tn = 1

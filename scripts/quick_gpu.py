@@ -16,6 +16,7 @@ ap.add_argument("--configs", default="default", help="comma list of option sets,
                 "(bm25_index_set_option names: tile_docs, splits, consumer_warps, cap, waves, no_theta_share)")
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--scale", type=float, default=1.0)
+ap.add_argument("--k", type=int, default=0, help="override top-k")
 ap.add_argument("--compress", action="store_true", help="bf16 / 4-byte packed postings")
 ap.add_argument("--sort-queries", action="store_true", help="order the batch by heaviest (lowest-id) term")
 args = ap.parse_args()
@@ -25,6 +26,8 @@ for wl in args.workloads.split(","):
     idx, q, k = synth.make_workload(wl, device="cuda", scale=args.scale)
     index = engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs)
     index.set_option("timing", 1)
+    if args.k:
+        k = args.k
     if args.compress:
         index.compress()
     if args.sort_queries:
