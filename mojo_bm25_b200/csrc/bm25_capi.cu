@@ -579,8 +579,10 @@ int launch_score(bm25_index* ix, const LaunchPlan& lp, const SearchArgs& a, int6
     return BM25_OK;
 }
 
+// k_segments, or -- when `order` is given -- k_segments_order: the same work plus the batch ordering
+// (k_query_order) in the last CTA of the same launch.
 int launch_segments(bm25_index* ix, const LaunchPlan& lp, const int32_t* d_queries, int64_t Q, int64_t T, int k,
-                    u64* theta_q, bool all_terms, cudaStream_t st) {
+                    u64* theta_q, bool all_terms, cudaStream_t st, const OrderArgs* order = nullptr) {
     const int64_t n_qt = Q * T;
     int rc = ix->ws_seg.reserve((size_t)n_qt * (lp.seg_rows + 1));
     if (rc) return rc;
@@ -588,10 +590,28 @@ int launch_segments(bm25_index* ix, const LaunchPlan& lp, const int32_t* d_queri
     int level = 0;
     while ((1 << level) < k) ++level;
     const bool prime = theta_q && ix->d_bounds && !lp.general && level < kBoundLevels && !ix->opt_no_priming;
-    const int64_t blocks = (n_qt * 32 + 255) / 256;
-    k_segments<<<(unsigned)blocks, 256, 0, st>>>(ix->d_tptr, all_terms ? nullptr : ix->d_term_row, ix->d_ids, d_queries,
-                                                 n_qt, (int)T, (int)ix->n_terms, lp.seg_docs, lp.seg_rows, ix->ws_seg.p,
-                                                 prime ? ix->d_bounds : nullptr, level, theta_q);
+    SegArgs g{};
+    g.tptr = ix->d_tptr;
+    g.term_row = all_terms ? nullptr : ix->d_term_row;
+    g.ids = ix->d_ids;
+    g.queries = d_queries;
+    g.n_qt = n_qt;
+    g.T = (int)T;
+    g.n_terms = (int)ix->n_terms;
+    g.row_docs = lp.seg_docs;
+    g.n_rows = lp.seg_rows;
+    g.seg = ix->ws_seg.p;
+    g.bounds = prime ? ix->d_bounds : nullptr;
+    g.level = level;
+    g.theta_q = theta_q;
+    if (order) {
+        const int64_t blocks = (n_qt * 32 + 1023) / 1024 + 1;  // + the ordering CTA
+        const size_t smem = order->P <= 4096 ? (size_t)std::max(order->P, 1024) * 8 : 0;
+        k_segments_order<<<(unsigned)blocks, 1024, smem, st>>>(g, *order);
+    } else {
+        const int64_t blocks = (n_qt * 32 + 255) / 256;
+        k_segments<<<(unsigned)blocks, 256, 0, st>>>(g);
+    }
     ++g_launches;
     CU(cudaGetLastError());
     return BM25_OK;
@@ -608,7 +628,10 @@ int launch_merge(const MergeArgs& m, int device, size_t smem_optin, cudaStream_t
         CU(cudaFuncSetAttribute(k_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
         configured[device % 64] = max_dyn;
     }
-    k_merge<<<(unsigned)m.Q, kThreads, smem, st>>>(m);
+    // CTA size follows the sort size: a 32-key merge (k = 10, two tile ranges) needs no 512 threads
+    int threads = kThreads;
+    while (threads > 64 && threads >= m.P) threads >>= 1;
+    k_merge<<<(unsigned)m.Q, threads, smem, st>>>(m);
     ++g_launches;
     CU(cudaGetLastError());
     return BM25_OK;
@@ -671,18 +694,26 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
         ix->ev_valid = false;
         CU(cudaEventRecord(ix->ev[0], st));
     }
-    if ((rc = launch_segments(ix, lp, d_queries, Q, T, k, ix->opt_no_theta_share ? nullptr : ix->ws_theta.p, false, st))) return rc;
-    // cross-query L2 sharing: CTAs of queries with the same heaviest term become neighbours
+    // cross-query L2 sharing: CTAs of queries with the same heaviest term become neighbours; the
+    // ordering runs in the same launch as the segment table
     const bool qsort = !ix->opt_no_query_sort && Q > 1 && Q <= (1 << 20);
+    OrderArgs o{};
     if (qsort) {
         const int P = next_pow2(Q);
         if ((rc = ix->ws_qperm.reserve((size_t)Q))) return rc;
         if (P > 4096 && (rc = ix->ws_qkey.reserve((size_t)P))) return rc;
-        k_query_order<<<1, 1024, P <= 4096 ? (size_t)std::max(P, 1024) * 8 : 0, st>>>(ix->d_tptr, d_queries, (int)Q, (int)T,
-                                                                      (int)ix->n_terms, P, ix->ws_qkey.p, ix->ws_qperm.p);
-        ++g_launches;
-        CU(cudaGetLastError());
+        o.tptr = ix->d_tptr;
+        o.queries = d_queries;
+        o.Q = (int)Q;
+        o.T = (int)T;
+        o.n_terms = (int)ix->n_terms;
+        o.P = P;
+        o.keys_g = ix->ws_qkey.p;
+        o.perm = ix->ws_qperm.p;
     }
+    if ((rc = launch_segments(ix, lp, d_queries, Q, T, k, ix->opt_no_theta_share ? nullptr : ix->ws_theta.p, false, st,
+                              qsort ? &o : nullptr)))
+        return rc;
     if (timing) CU(cudaEventRecord(ix->ev[1], st));
     SearchArgs a{};
     a.ids = ix->d_ids;

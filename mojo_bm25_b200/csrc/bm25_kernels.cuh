@@ -12,7 +12,8 @@
 //   k_term_bounds[_exact] load time: per-term weight order statistics (threshold priming)
 //   k_segments           per (query, term): threshold priming; cursor starts of the light terms for
 //                        every document chunk (binary search on doc id inside the term's posting list)
-//   k_query_order        per batch: queries with the same heaviest term become neighbours (L2 sharing)
+//   k_query_order        per batch: queries with the same heaviest term become neighbours (L2 sharing);
+//                        normally launched together with k_segments as k_segments_order
 //   k_score_topk_s       (query width <= 32) / k_score_topk (any width): one warp per (query, document
 //                        chunk): private shared-memory score tile, in-order accumulation (heavy terms:
 //                        table-addressed 16-byte vector loads, PTX read-modify-write; light terms:
@@ -211,16 +212,27 @@ __global__ void __launch_bounds__(256) k_pack(const int32_t* __restrict__ ids, c
 //    search on doc id inside the term's list).  Terms with a row in the tile table are skipped
 //    when `term_row` is given: the score kernel never reads their cursor starts.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_segments(const int2* __restrict__ tptr, const int32_t* __restrict__ term_row,
-                                                  const int32_t* __restrict__ ids,
-                                                  const int32_t* __restrict__ queries, int64_t n_qt,
-                                                  int T, int n_terms, int row_docs, int n_rows,
-                                                  int32_t* __restrict__ seg,
-                                                  const float* __restrict__ bounds, int level,
-                                                  u64* __restrict__ theta_q) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (warp >= n_qt) return;
+struct SegArgs {
+    const int2* __restrict__ tptr;
+    const int32_t* __restrict__ term_row;
+    const int32_t* __restrict__ ids;
+    const int32_t* __restrict__ queries;
+    int64_t n_qt;
+    int T, n_terms, row_docs, n_rows;
+    int32_t* __restrict__ seg;
+    const float* __restrict__ bounds;
+    int level;
+    u64* __restrict__ theta_q;
+};
+__device__ __forceinline__ void segments_warp(const SegArgs& g, int64_t warp, int lane) {
+    const int2* __restrict__ tptr = g.tptr;
+    const int32_t* __restrict__ term_row = g.term_row;
+    const int32_t* __restrict__ ids = g.ids;
+    const int32_t* __restrict__ queries = g.queries;
+    const int T = g.T, n_terms = g.n_terms, row_docs = g.row_docs, n_rows = g.n_rows, level = g.level;
+    int32_t* __restrict__ seg = g.seg;
+    const float* __restrict__ bounds = g.bounds;
+    u64* __restrict__ theta_q = g.theta_q;
     const int term = queries[warp];
     const int64_t q = warp / T;
     const int t = (int)(warp - q * T);
@@ -256,6 +268,12 @@ __global__ void __launch_bounds__(256) k_segments(const int2* __restrict__ tptr,
         }
         out[(int64_t)j * T] = res;
     }
+}
+
+__global__ void __launch_bounds__(256) k_segments(const SegArgs g) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= g.n_qt) return;
+    segments_warp(g, warp, threadIdx.x & 31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -406,9 +424,19 @@ __device__ __forceinline__ void select_candidates(u64* cand, int n, int k, u64* 
 // One CTA; key = (heaviest term id << 32 | query); bitonic sort in shared memory (P <= 4096) or
 // in global memory; perm[i] = query run by the i-th group of CTAs.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_query_order(const int2* __restrict__ tptr, const int32_t* __restrict__ queries,
-                                                      int Q, int T, int n_terms, int P, u64* __restrict__ keys_g,
-                                                      int32_t* __restrict__ perm) {
+struct OrderArgs {
+    const int2* __restrict__ tptr;
+    const int32_t* __restrict__ queries;
+    int Q, T, n_terms, P;
+    u64* __restrict__ keys_g;
+    int32_t* __restrict__ perm;
+};
+__device__ __forceinline__ void query_order_cta(const OrderArgs& o) {  // one CTA of 1024 threads
+    const int2* __restrict__ tptr = o.tptr;
+    const int32_t* __restrict__ queries = o.queries;
+    const int Q = o.Q, T = o.T, n_terms = o.n_terms, P = o.P;
+    u64* __restrict__ keys_g = o.keys_g;
+    int32_t* __restrict__ perm = o.perm;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* keys = (P <= 4096) ? reinterpret_cast<u64*>(smem_raw) : keys_g;
     const int tid = threadIdx.x;
@@ -465,6 +493,18 @@ __global__ void __launch_bounds__(1024) k_query_order(const int2* __restrict__ t
         }
     }
     for (int i = tid; i < Q; i += 1024) perm[i] = (int32_t)(uint32_t)keys[i];
+}
+
+// k_segments and the batch ordering in ONE launch (they are independent): the last CTA orders the batch
+// while the others (32 warps each) prime the thresholds and search the cursor starts.
+__global__ void __launch_bounds__(1024) k_segments_order(const SegArgs g, const OrderArgs o) {
+    if (blockIdx.x == gridDim.x - 1) {
+        query_order_cta(o);
+        return;
+    }
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= g.n_qt) return;
+    segments_warp(g, warp, threadIdx.x & 31);
 }
 
 struct SearchArgs {
@@ -1725,6 +1765,7 @@ __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
     u64* buf = reinterpret_cast<u64*>(smem_raw);
     unsigned char* present = reinterpret_cast<unsigned char*>(buf + a.P);
     const int tid = threadIdx.x;
+    const int nt = blockDim.x;  // 64 .. kThreads: small merges run in small CTAs (more of them per SM)
     const int64_t q = blockIdx.x;
     const int total = a.n_lists * a.k_in;
     const int keep = a.k_out;
@@ -1734,7 +1775,7 @@ __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
     while (next < total || have == 0) {
         const int room = a.P - have;
         const int take = min(room, total - next);
-        for (int i = tid; i < room; i += kThreads) {
+        for (int i = tid; i < room; i += nt) {
             u64 key = 0;
             if (i < take) {
                 const int e = next + i;
@@ -1750,7 +1791,7 @@ __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
             buf[have + i] = key;
         }
         __syncthreads();
-        bitonic_sort_desc(buf, a.P, CtaGroup{kThreads, tid});
+        bitonic_sort_desc(buf, a.P, CtaGroup{nt, tid});
         next += take;
         have = min(keep, a.P);
         if (take == 0) break;
@@ -1759,10 +1800,10 @@ __global__ void __launch_bounds__(kThreads) k_merge(const MergeArgs a) {
     // count valid among the first keep
     __shared__ int s_valid;
     if (tid == 0) s_valid = 0;
-    for (int i = tid; i < keep; i += kThreads) present[i] = 0;
+    for (int i = tid; i < keep; i += nt) present[i] = 0;
     __syncthreads();
     int local = 0;
-    for (int i = tid; i < keep; i += kThreads) {
+    for (int i = tid; i < keep; i += nt) {
         const u64 key = buf[i];
         if (key != 0) {
             ++local;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Turn the ncu reports of scripts/profile_all.sh (gpurun_out/<tag>_*.ncu-rep) into the committed text summaries.
 TAG=${1:-r2}
-for WL in B 10M E C; do
+for WL in B 10M E C 10M_bf16; do
   R=gpurun_out/${TAG}_score_$WL.ncu-rep
   [ -f $R ] || continue
   python scripts/ncu_summary.py $R > profiles/${TAG}_score_${WL}_summary.txt

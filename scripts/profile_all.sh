@@ -11,7 +11,10 @@ for WL in B 10M E C; do
   ncu --set full --clock-control none --import-source on -k regex:k_score_topk -s 2 -c 1 -o gpurun_out/${TAG}_score_$WL \
       python scripts/quick_gpu.py --workloads $WL --iters 1 > gpurun_out/ncu_$WL.log 2>&1
 done
+python scripts/quick_gpu.py --workloads 10M --iters 1 --compress > gpurun_out/plain_10M_bf16.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:k_score_topk -s 2 -c 1 -o gpurun_out/${TAG}_score_10M_bf16 \
+    python scripts/quick_gpu.py --workloads 10M --iters 1 --compress > gpurun_out/ncu_10M_bf16.log 2>&1
 python scripts/quick_gpu.py --workloads 10M --iters 1 > gpurun_out/plain_aux.log 2>&1 &&
-ncu --set full --clock-control none -k "regex:k_segments|k_merge|k_query_order" -s 6 -c 3 -o gpurun_out/${TAG}_aux_10M \
+ncu --set full --clock-control none -k "regex:k_segments|k_merge" -s 4 -c 2 -o gpurun_out/${TAG}_aux_10M \
     python scripts/quick_gpu.py --workloads 10M --iters 1 > gpurun_out/ncu_aux.log 2>&1
 ls -la gpurun_out/${TAG}_*
