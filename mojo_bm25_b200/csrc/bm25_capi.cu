@@ -1111,6 +1111,22 @@ int bm25_search_host(bm25_index* ix, const int32_t* h_queries, int64_t Q, int64_
     CU(cudaMemcpyAsync(ix->ws_queries.p, ix->pin_queries.p, nq * 4, cudaMemcpyHostToDevice, st));
     float* d_scores = reinterpret_cast<float*>(ix->ws_out_ids.p + no);
     if ((rc = search_locked(ix, ix->ws_queries.p, Q, T, k, ix->ws_out_ids.p, d_scores, st))) return rc;
+    // caller buffers in page-locked memory (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory)
+    // receive the results by DMA directly; pageable buffers go through the handle's pinned staging area
+    cudaPointerAttributes pa_i, pa_s;
+    const bool direct = cudaPointerGetAttributes(&pa_i, h_out_ids) == cudaSuccess && pa_i.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&pa_s, h_out_scores) == cudaSuccess && pa_s.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (direct) {
+        if (reinterpret_cast<const int32_t*>(h_out_scores) == h_out_ids + no) {  // one contiguous [2][Q][k] block
+            CU(cudaMemcpyAsync(h_out_ids, ix->ws_out_ids.p, 2 * no * 4, cudaMemcpyDeviceToHost, st));
+        } else {
+            CU(cudaMemcpyAsync(h_out_ids, ix->ws_out_ids.p, no * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_out_scores, d_scores, no * 4, cudaMemcpyDeviceToHost, st));
+        }
+        CU(cudaStreamSynchronize(st));
+        return BM25_OK;
+    }
     CU(cudaMemcpyAsync(ix->pin_out_ids.p, ix->ws_out_ids.p, 2 * no * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     memcpy(h_out_ids, ix->pin_out_ids.p, no * 4);

@@ -34,6 +34,18 @@ def _ptr(a: np.ndarray):
     return ctypes.c_void_p(a.ctypes.data)
 
 
+def _pinned_outputs(qn: int, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """(ids int32 [Q,k], scores fp32 [Q,k]) as numpy views of ONE fresh page-locked block [2,Q,k]:
+    ``bm25_search_host`` then delivers the results with a single DMA and no staging copy.  The
+    block comes from torch's caching host allocator and lives as long as either array does."""
+    if qn * k == 0:
+        return np.empty((qn, k), np.int32), np.empty((qn, k), np.float32)
+    import torch
+
+    block = torch.empty((2, qn, k), dtype=torch.int32, pin_memory=True).numpy()
+    return block[0], block[1].view(np.float32)
+
+
 def round_to_bf16(data) -> np.ndarray:
     """fp32 array -> the fp32 values a compressed (bf16) handle stores: round to nearest even on the
     upper 16 bits.  Host-side twin of the library's k_quantize, for callers who want to know exactly
@@ -147,8 +159,7 @@ class DeviceIndex:
         if q.ndim != 2:
             raise ValueError("queries must be 2-D [Q, T]")
         qn, tn = q.shape
-        ids = np.empty((qn, int(k)), np.int32)  # fully overwritten by the library
-        scores = np.empty((qn, int(k)), np.float32)
+        ids, scores = _pinned_outputs(qn, int(k))  # fully overwritten by the library
         if tn == 0:
             q = np.full((qn, 1), -1, np.int32)
             tn = 1
