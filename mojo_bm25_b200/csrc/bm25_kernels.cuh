@@ -881,7 +881,7 @@ __device__ __noinline__ float tile_finish(const ColdCtx c, int base, int nd_w, i
             __syncwarp();
         }
         left = __any_sync(kFull, left);
-        if (!left) tile_clear(c.scw, c.S, lane);
+        if (!left) smem_bulk_zero(smem_u32(c.scw), (unsigned)c.S * 4u);  // one st.bulk instead of 16 vector stores per lane
     }
     left = __any_sync(kFull, left);
     if (left || ld_volatile(&c.sh->overflow)) {
