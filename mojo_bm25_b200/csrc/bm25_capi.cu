@@ -147,6 +147,21 @@ int check_device(int device, cudaDeviceProp* prop) {
 
 }  // namespace
 
+struct TileTableSet {
+    int32_t* d_term_row = nullptr;  // [n_terms] tile-table row or -1
+    int32_t* d_tab = nullptr;       // [n_heavy, tab_tiles + 1]
+    int64_t n_heavy = 0, tab_bytes = 0;
+    int tab_tile_docs = 0, tab_heavy_min = 0;  // what the table was built for (0 = not built)
+    uint32_t* d_pk = nullptr;       // compressed handles: [nnz_padded] packed postings for pk_tile_docs documents per tile
+    int pk_tile_docs = 0;
+    void release() {
+        if (d_term_row) cudaFree(d_term_row);
+        if (d_tab) cudaFree(d_tab);
+        if (d_pk) cudaFree(d_pk);
+        *this = TileTableSet{};
+    }
+};
+
 struct bm25_index {
     int device = 0;
     int sm_count = 148;
@@ -158,15 +173,12 @@ struct bm25_index {
     float2* d_wrange = nullptr;     // [n_terms] {smallest, largest} weight of the term
     int32_t* d_ids = nullptr;       // [nnz_padded]
     float* d_w = nullptr;           // [nnz_padded]
-    int32_t* d_term_row = nullptr;  // [n_terms] tile-table row or -1
-    int32_t* d_tab = nullptr;       // [n_heavy, tab_tiles + 1]
-    int64_t n_heavy = 0, tab_bytes = 0;
-    int tab_tile_docs = 0, tab_heavy_min = 0;  // what the table was built for (0 = not built)
+    // everything that depends on the tile size: the active set and one stashed set, so that a handle
+    // serving two query shapes with different tile sizes (launch plan) does not rebuild on every switch
+    TileTableSet tt, tt_stash;
     float* d_bounds = nullptr;  // [n_terms][kBoundLevels] per-term weight order statistics (threshold priming)
     // compressed index (bm25_index_compress): weights rounded to bf16, 4-byte packed postings
     int weight_format = BM25_WEIGHTS_FP32;
-    uint32_t* d_pk = nullptr;  // [nnz_padded] packed postings for pk_tile_docs documents per tile
-    int pk_tile_docs = 0;
     std::vector<int32_t> h_indptr;  // host copy for byte accounting / heavy-term selection
     // options (0 = auto)
     int opt_tile_docs = 0, opt_splits = 0, opt_force_general = 0, opt_timing = 0;
@@ -198,7 +210,9 @@ struct bm25_index {
     }
     int n_tiles() const { return (int)std::max<int64_t>(1, (n_docs + tile_docs() - 1) / tile_docs()); }
     int64_t device_bytes() const {
-        int64_t b = n_terms * 12 + nnz_padded * 8 + tab_bytes + (d_pk ? nnz_padded * 4 : 0);
+        int64_t b = n_terms * 8 + nnz_padded * 8;
+        for (const TileTableSet* t : {&tt, &tt_stash})
+            b += t->tab_bytes + (t->d_term_row ? n_terms * 4 : 0) + (t->d_pk ? nnz_padded * 4 : 0);
         if (d_bounds) b += n_terms * kBoundLevels * 4;
         b += ws_seg.bytes() + ws_partial.bytes() + ws_theta.bytes() + ws_cand.bytes() + ws_qkey.bytes() + ws_qperm.bytes() + ws_queries.bytes() + ws_out_ids.bytes() +
              ws_out_scores.bytes();
@@ -272,7 +286,6 @@ int finish_create(bm25_index* ix, const cudaDeviceProp& prop, const int32_t* d_i
     if (cudaMalloc(&ix->d_tptr, (size_t)std::max<int64_t>(V, 1) * sizeof(int2)) != cudaSuccess ||
         cudaMalloc(&ix->d_ids, (size_t)(pos + 4) * 4) != cudaSuccess ||
         cudaMalloc(&ix->d_w, (size_t)(pos + 4) * 4) != cudaSuccess ||
-        cudaMalloc(&ix->d_term_row, (size_t)std::max<int64_t>(V, 1) * 4) != cudaSuccess ||
         cudaMalloc(&ix->d_wrange, (size_t)std::max<int64_t>(V, 1) * sizeof(float2)) != cudaSuccess) {
         cudaGetLastError();
         return fail(BM25_ERR_OOM, "cudaMalloc of the index (%lld postings) failed", (long long)ix->nnz);
@@ -294,8 +307,16 @@ int finish_create(bm25_index* ix, const cudaDeviceProp& prop, const int32_t* d_i
 // heavy when df * 16 >= heavy_min * n_tiles.
 int ensure_table(bm25_index* ix, int S) {
     int hm = ix->opt_heavy_min > 0 ? ix->opt_heavy_min : 16;
-    if (ix->tab_tile_docs == S && ix->tab_heavy_min == hm) return BM25_OK;
-    CU(cudaDeviceSynchronize());  // no search may still be reading the old table
+    if (ix->tt.tab_tile_docs == S && ix->tt.tab_heavy_min == hm) return BM25_OK;
+    if (ix->tt_stash.tab_tile_docs == S && ix->tt_stash.tab_heavy_min == hm) {
+        std::swap(ix->tt, ix->tt_stash);  // nothing is freed: searches in flight keep valid pointers
+        return BM25_OK;
+    }
+    CU(cudaDeviceSynchronize());  // no search may still be reading the set that is evicted
+    ix->tt_stash.release();
+    if (ix->tt.tab_tile_docs) std::swap(ix->tt, ix->tt_stash);
+    TileTableSet& tt = ix->tt;
+    tt.release();
     const int64_t V = ix->n_terms;
     const int64_t NB = std::max<int64_t>(1, (ix->n_docs + S - 1) / S);
     std::vector<int32_t> row((size_t)std::max<int64_t>(V, 1), -1), heavy;
@@ -311,56 +332,60 @@ int ensure_table(bm25_index* ix, int S) {
         eff *= 2;
     }
     for (size_t r = 0; r < heavy.size(); ++r) row[heavy[r]] = (int32_t)r;
-    if (ix->d_tab) cudaFree(ix->d_tab);
-    ix->d_tab = nullptr;
-    ix->tab_bytes = 0;
-    ix->tab_tile_docs = 0;
     const int64_t entries = (int64_t)heavy.size() * (NB + 1);
-    if (V > 0) CU(cudaMemcpy(ix->d_term_row, row.data(), (size_t)V * 4, cudaMemcpyHostToDevice));
+    if (cudaMalloc(&tt.d_term_row, (size_t)std::max<int64_t>(V, 1) * 4) != cudaSuccess) {
+        cudaGetLastError();
+        tt.d_term_row = nullptr;
+        return fail(BM25_ERR_OOM, "cudaMalloc of the term-row map failed");
+    }
+    if (V > 0) CU(cudaMemcpy(tt.d_term_row, row.data(), (size_t)V * 4, cudaMemcpyHostToDevice));
     if (entries > 0) {
         int32_t* d_heavy = nullptr;
-        if (cudaMalloc(&ix->d_tab, (size_t)entries * 4) != cudaSuccess ||
+        if (cudaMalloc(&tt.d_tab, (size_t)entries * 4) != cudaSuccess ||
             cudaMalloc(&d_heavy, heavy.size() * 4) != cudaSuccess) {
             cudaGetLastError();
-            if (ix->d_tab) cudaFree(ix->d_tab);
-            ix->d_tab = nullptr;
+            tt.release();
             return fail(BM25_ERR_OOM, "cudaMalloc of the tile table (%lld entries) failed", (long long)entries);
         }
         cudaMemcpy(d_heavy, heavy.data(), heavy.size() * 4, cudaMemcpyHostToDevice);
         k_build_table<<<(unsigned)((entries + 255) / 256), 256>>>(ix->d_tptr, d_heavy, ix->d_ids, entries, (int)NB, S,
-                                                                  ix->d_tab);
+                                                                  tt.d_tab);
         ++g_launches;
         cudaError_t e = cudaDeviceSynchronize();
         cudaFree(d_heavy);
-        if (e != cudaSuccess) return fail(BM25_ERR_CUDA, "building the tile table failed: %s", cudaGetErrorString(e));
+        if (e != cudaSuccess) {
+            tt.release();
+            return fail(BM25_ERR_CUDA, "building the tile table failed: %s", cudaGetErrorString(e));
+        }
     }
-    ix->n_heavy = (int64_t)heavy.size();
-    ix->tab_bytes = entries * 4;
-    ix->tab_tile_docs = S;
-    ix->tab_heavy_min = hm;
+    tt.n_heavy = (int64_t)heavy.size();
+    tt.tab_bytes = entries * 4;
+    tt.tab_tile_docs = S;
+    tt.tab_heavy_min = hm;
     return BM25_OK;
 }
 
 // Compressed handles: the 4-byte packed postings for S documents per tile (rebuilt with the tile size).
-int ensure_packed(bm25_index* ix, int S) {
-    if (ix->weight_format == BM25_WEIGHTS_FP32 || ix->pk_tile_docs == S) return BM25_OK;
+int ensure_packed(bm25_index* ix, int S) {  // after ensure_table(ix, S): packs for the active set
+    TileTableSet& tt = ix->tt;
+    if (ix->weight_format == BM25_WEIGHTS_FP32 || tt.pk_tile_docs == S) return BM25_OK;
     if (S > kPkMaxTileDocs)
         return fail(BM25_ERR_UNSUPPORTED, "a compressed index needs tile_docs <= %d (16-bit tile-local slots), got %d",
                     kPkMaxTileDocs, S);
     CU(cudaDeviceSynchronize());  // no search may still be reading the old array
-    if (!ix->d_pk && cudaMalloc(&ix->d_pk, (size_t)(ix->nnz_padded + 4) * 4) != cudaSuccess) {
+    if (!tt.d_pk && cudaMalloc(&tt.d_pk, (size_t)(ix->nnz_padded + 4) * 4) != cudaSuccess) {
         cudaGetLastError();
-        ix->d_pk = nullptr;
+        tt.d_pk = nullptr;
         return fail(BM25_ERR_OOM, "cudaMalloc of the packed postings (%lld) failed", (long long)ix->nnz_padded);
     }
-    ix->pk_tile_docs = 0;
+    tt.pk_tile_docs = 0;
     if (ix->nnz_padded > 0) {
-        k_pack<<<ix->sm_count * 8, 256>>>(ix->d_ids, ix->d_w, ix->nnz_padded, S, ix->d_pk);
+        k_pack<<<ix->sm_count * 8, 256>>>(ix->d_ids, ix->d_w, ix->nnz_padded, S, tt.d_pk);
         ++g_launches;
         CU(cudaGetLastError());
         CU(cudaDeviceSynchronize());
     }
-    ix->pk_tile_docs = S;
+    tt.pk_tile_docs = S;
     return BM25_OK;
 }
 
@@ -477,19 +502,28 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
     // large k: the candidate buffer moves to global memory (see the kernel); it is then compacted by
     // radix select only, which needs cap > kSelectMin
     lp->cand_global = (k > kSelectMin && !ix->opt_cand_smem) ? 1 : 0;
-    // wide queries (T ~ 64) need so much cursor state that only two 8-warp CTAs fit on an SM: take the
-    // warp count (8, 7 or 6) that keeps the most warps resident (E: 3 x 7 = 21 instead of 2 x 8 = 16)
+    // wide queries (T ~ 64) need so much cursor state that only two 8-warp CTAs with 2048-document tiles
+    // fit on an SM: take the warp count (8, 7 or 6) and, when the tile size is automatic, the tile size
+    // (2048 or 1792 documents) that keep the most warps resident (E: 3 x 8 warps on 1792-document tiles
+    // instead of 3 x 7 on 2048: -3 %); ties go to the larger tile, then to more warps per CTA
     if (ix->opt_warps <= 0) {
-        int best_w = lp->warps, best_res = 0;
-        for (int w = lp->warps; w >= 6; --w) {
-            const size_t sm = score_smem(lp->tile_docs, lp->cand_global ? 0 : lp->cap, T, w) + 1024 + 1152;
-            const int res = (int)std::min<size_t>(ix->smem_per_sm / sm, 2048 / (w * 32)) * w;
-            if (res > best_res) {
-                best_res = res;
-                best_w = w;
+        int best_w = lp->warps, best_s = lp->tile_docs, best_res = 0;
+        const int s_lo = (ix->opt_tile_docs <= 0 && lp->tile_docs == 2048) ? 1792 : lp->tile_docs;
+        for (int sd = lp->tile_docs; sd >= s_lo; sd -= 256) {
+            for (int w = lp->warps; w >= 6; --w) {
+                const size_t sm = score_smem(sd, lp->cand_global ? 0 : lp->cap, T, w) + 1024 + 1152;
+                // CTAs per SM: shared memory, thread slots, and the register file (80 registers per thread)
+                const size_t ctas = std::min<size_t>(std::min<size_t>(ix->smem_per_sm / sm, 2048 / (w * 32)), 65536 / (80 * 32 * w));
+                const int res = (int)ctas * w;
+                if (res > best_res) {
+                    best_res = res;
+                    best_w = w;
+                    best_s = sd;
+                }
             }
         }
         lp->warps = best_w;
+        lp->tile_docs = best_s;
     }
     // shrink the CTA (fewer warps, then smaller tiles) until it fits into shared memory
     const size_t hard = ix->smem_optin - 1024;
@@ -523,6 +557,9 @@ int make_plan(bm25_index* ix, int64_t Q, int64_t T, int k, LaunchPlan* lp) {
     lp->seg_docs = lp->tiles_per_chunk * lp->tile_docs;
     lp->seg_rows = lp->n_chunks;
     plan_mode(ix, lp);
+    if (getenv("BM25_B200_DEBUG_PLAN"))
+        fprintf(stderr, "plan: tile_docs=%d warps=%d splits=%d tiles_per_chunk=%d n_chunks=%d cap=%d smem=%zu cand_global=%d smem_per_sm=%zu\n",
+                lp->tile_docs, lp->warps, lp->splits, lp->tiles_per_chunk, lp->n_chunks, lp->cap, lp->smem, lp->cand_global, ix->smem_per_sm);
     return BM25_OK;
 }
 
@@ -592,7 +629,7 @@ int launch_segments(bm25_index* ix, const LaunchPlan& lp, const int32_t* d_queri
     const bool prime = theta_q && ix->d_bounds && !lp.general && level < kBoundLevels && !ix->opt_no_priming;
     SegArgs g{};
     g.tptr = ix->d_tptr;
-    g.term_row = all_terms ? nullptr : ix->d_term_row;
+    g.term_row = all_terms ? nullptr : ix->tt.d_term_row;
     g.ids = ix->d_ids;
     g.queries = d_queries;
     g.n_qt = n_qt;
@@ -718,8 +755,8 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     SearchArgs a{};
     a.ids = ix->d_ids;
     a.w = ix->d_w;
-    a.term_row = ix->d_term_row;
-    a.tab = ix->d_tab;
+    a.term_row = ix->tt.d_term_row;
+    a.tab = ix->tt.d_tab;
     a.queries = d_queries;
     a.qperm = qsort ? ix->ws_qperm.p : nullptr;
     a.seg = ix->ws_seg.p;
@@ -747,7 +784,7 @@ int search_locked(bm25_index* ix, const int32_t* d_queries, int64_t Q, int64_t T
     a.bulk_clear = ix->opt_no_bulk_clear ? 0 : 1;
     a.wrange = ix->d_wrange;
     a.no_epoch = ix->opt_no_epoch;
-    a.pk = (ix->weight_format != BM25_WEIGHTS_FP32 && !ix->opt_no_packed) ? ix->d_pk : nullptr;
+    a.pk = (ix->weight_format != BM25_WEIGHTS_FP32 && !ix->opt_no_packed) ? ix->tt.d_pk : nullptr;
     if ((rc = launch_score(ix, lp, a, Q, false, st))) return rc;
     if (timing) CU(cudaEventRecord(ix->ev[2], st));
     MergeArgs m{};
@@ -953,7 +990,8 @@ int bm25_index_compress(bm25_index* ix, int weight_format) {
         if (h_flags[0]) ix->all_positive = false;  // a weight rounded to zero: every document competes
     }
     ix->weight_format = weight_format;
-    ix->pk_tile_docs = 0;
+    ix->tt.pk_tile_docs = 0;  // packed from the rounded weights on the next search
+    ix->tt_stash.pk_tile_docs = 0;
     int rc = compute_bounds(ix);
     if (rc) return rc;
     CU(cudaDeviceSynchronize());
@@ -968,10 +1006,9 @@ int bm25_index_destroy(bm25_index* ix) {
         if (ix->d_ids) cudaFree(ix->d_ids);
         if (ix->d_wrange) cudaFree(ix->d_wrange);
         if (ix->d_w) cudaFree(ix->d_w);
-        if (ix->d_term_row) cudaFree(ix->d_term_row);
-        if (ix->d_tab) cudaFree(ix->d_tab);
+        ix->tt.release();
+        ix->tt_stash.release();
         if (ix->d_bounds) cudaFree(ix->d_bounds);
-        if (ix->d_pk) cudaFree(ix->d_pk);
         if (ix->ws_done) cudaEventDestroy(ix->ws_done);
         ix->ws_seg.release();
         ix->ws_partial.release();

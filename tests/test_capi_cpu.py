@@ -82,3 +82,23 @@ def test_int64_index_arrays_are_range_checked_before_the_int32_cast():
         engine.DeviceIndex(np.array([0, 1], np.int64), np.array([2 ** 40], np.int64), np.ones(1, np.float32), n_docs=10)
     with pytest.raises(ValueError, match="integer"):
         engine.DeviceIndex(np.array([0.0, 1.0]), np.array([0], np.int64), np.ones(1, np.float32), n_docs=10)
+
+
+def test_round_to_bf16_is_round_to_nearest_even():
+    """Host-side twin of k_quantize (compressed handles): round to nearest even on the upper 16 bits,
+    the same values torch's float32 -> bfloat16 conversion produces."""
+    import numpy as np
+    import torch
+
+    from mojo_bm25_b200 import engine
+
+    x = np.array([1.0, 1.00390625, 1.005859375, 1.01171875, 3.1415927, 1e-30, 6.5e4], np.float32)
+    r = engine.round_to_bf16(x)
+    assert np.all((r.view(np.uint32) & 0xFFFF) == 0)
+    # ties go to the even mantissa: 1 + 2^-8 -> 1.0, 1 + 3*2^-8 -> 1 + 2^-6; 1 + 3*2^-9 rounds up to 1 + 2^-7
+    assert r[1] == np.float32(1.0) and r[2] == np.float32(1.0078125) and r[3] == np.float32(1.015625)
+    assert np.all(np.abs(r - x) <= np.abs(x) * 2.0 ** -8)
+    rng = np.random.default_rng(0)
+    y = (rng.standard_normal(100000) * 10.0 ** rng.uniform(-20, 20, 100000)).astype(np.float32)
+    t = torch.from_numpy(y).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(t.view(np.uint32), engine.round_to_bf16(y).view(np.uint32))

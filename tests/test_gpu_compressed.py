@@ -31,19 +31,6 @@ def _check(index, indptr, indices, data_q, n_docs, queries, k):
     return ids, sc
 
 
-def test_round_to_bf16_is_round_to_nearest_even(engine):
-    x = np.array([1.0, 1.00390625, 1.005859375, 1.01171875, 3.1415927, 1e-30, 6.5e4], np.float32)
-    r = engine.round_to_bf16(x)
-    assert np.all((r.view(np.uint32) & 0xFFFF) == 0)
-    # ties go to the even mantissa: 1 + 2^-8 -> 1.0, 1 + 3*2^-8 -> 1 + 2^-6; 1 + 3*2^-9 rounds up to 1 + 2^-7
-    assert r[1] == np.float32(1.0) and r[2] == np.float32(1.0078125) and r[3] == np.float32(1.015625)
-    assert np.all(np.abs(r - x) <= np.abs(x) * 2.0 ** -8)
-    import torch
-
-    t = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
-    assert np.array_equal(t.view(np.uint32), r.view(np.uint32))
-
-
 @pytest.mark.parametrize("workload,scale,k", [("tiny", 1.0, 10), ("B", 0.05, 10), ("B", 0.05, 100),
                                               ("C", 0.005, 100), ("10Mc", 0.01, 100), ("E", 0.03, 1000)])
 def test_compressed_index_equals_oracle_on_rounded_weights(engine, workload, scale, k):
