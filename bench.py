@@ -332,8 +332,25 @@ def kernel_split(ctx, indexes, step, steps):
     return np.median(np.array(rows), axis=0)  # median: one slow launch (e.g. a clock ramp after the sync) must not move it
 
 
-def roofline_record(ctx, posting_bytes, km, batch_bytes, ms_per_step):
+def measured_traffic(workload):
+    """DRAM bytes per launch of the score kernel from the committed ncu --set full capture of this
+    workload (profiles/r2_traffic.json, written by scripts/ncu_traffic.py) -- reported only while the
+    capture's source stamp matches the kernel sources this run was built from; otherwise None."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import ncu_traffic
+
+        t = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+        if t.get("kernel_source_sha256") != ncu_traffic.source_stamp() or workload not in t:
+            return None, "no ncu capture of these kernel sources for this workload"
+        return t[workload]["dram_read"] + t[workload]["dram_write"], "profiles/r2_traffic.json (ncu --set full capture of the same kernel sources)"
+    except Exception as e:  # noqa: BLE001
+        return None, f"unavailable ({type(e).__name__})"
+
+
+def roofline_record(ctx, posting_bytes, km, batch_bytes, ms_per_step, traffic_key=None):
     score_ms = float(km[1])
+    traffic, traffic_src = measured_traffic(traffic_key) if traffic_key else (None, "no capture for this record")
     achieved = posting_bytes / (score_ms * 1e-3) / 1e9
     return {
         "bound": "hbm", "kernel": "k_score_topk (score accumulation + per-range top-k)",
@@ -343,9 +360,8 @@ def roofline_record(ctx, posting_bytes, km, batch_bytes, ms_per_step):
         "kernel_share_of_step": score_ms / float(km.sum()),
         "other_kernels_ms": {"k_segments+k_query_order": float(km[0]), "k_merge": float(km[2])},
         "whole_batch_GBps": batch_bytes / (ms_per_step * 1e-3) / 1e9,
-        # DRAM bytes per launch need a profiler; the ncu captures are committed under profiles/
-        # (r2_*_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum) -- nothing static is copied here
-        "traffic": None,
+        # DRAM bytes per launch need a profiler: taken from the committed ncu capture of the same sources
+        "traffic": traffic, "traffic_source": traffic_src,
     }
 
 
@@ -371,7 +387,7 @@ def e2e_host(ctx, index, qn, k, steps, units):
             "d2h_bytes_per_step": int(hid.nbytes + hsc.nbytes), "api": "bm25_search_host via DeviceIndex.search"}
 
 
-def measure_single(ctx, index, q, k, steps, warmup, want_e2e=True):
+def measure_single(ctx, index, q, k, steps, warmup, want_e2e=True, traffic_key=None):
     """One index on this rank, this rank's batch `q`: value / roofline / e2e of one workload."""
     import torch
 
@@ -389,7 +405,7 @@ def measure_single(ctx, index, q, k, steps, warmup, want_e2e=True):
     units = n_q * ctx.world  # query-split: every rank answers its own batch
     rec = {
         "value": units / (ms_per_step / 1e3), "ms_per_step": ms_per_step, "steps": steps,
-        "roofline": roofline_record(ctx, posting_bytes, km, posting_bytes + 8 * k * n_q, ms_per_step),
+        "roofline": roofline_record(ctx, posting_bytes, km, posting_bytes + 8 * k * n_q, ms_per_step, traffic_key),
         "step_ms_min": float(min(step_ms)), "step_ms_median": float(sorted(step_ms)[len(step_ms) // 2]),
         "wall_s_timed_region": wall,
     }
@@ -419,7 +435,9 @@ def sub_workload(ctx, name, k=0, steps=10, warmup=3, index=None, idx=None, compr
                                 heavy_range=cfg.get("heavy_range", 100))
         k0 = min(cfg["k"], idx.n_docs)
     k = k or k0
-    rec = measure_single(ctx, index, q, k, steps, warmup)
+    # the ncu captures are of the workloads' own k on one GPU (scripts/profile_all.sh)
+    tkey = (name + ("_bf16" if compress else "")) if (k == k0 and ctx.args.scale == 1.0) else None
+    rec = measure_single(ctx, index, q, k, steps, warmup, traffic_key=tkey)
     mode = "single" if ctx.world == 1 else "query-split"
     rec["config"] = workload_config(args, name, idx.n_docs, idx.n_terms, idx.nnz, int(q.shape[0]), int(q.shape[1]), k,
                                     synth.WORKLOADS[name].get("r0", 8), mode, ctx.world, 1)
@@ -582,7 +600,8 @@ def run_ours(args):
         if args.k:
             k = args.k
         index = engine.DeviceIndex.from_torch(idx.indptr, idx.indices, idx.data, idx.n_docs)
-        rec = measure_single(ctx, index, q, k, args.steps, args.warmup)
+        rec = measure_single(ctx, index, q, k, args.steps, args.warmup,
+                             traffic_key=args.workload if (args.scale == 1.0 and not args.k) else None)
         launches = engine.kernel_launches() - launches0  # headline only: timed loop + kernel-split pass + e2e
         n_q = int(q.shape[0])
         shape = (idx.n_docs, idx.n_terms, idx.nnz)

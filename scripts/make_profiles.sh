@@ -11,3 +11,4 @@ done
 [ -f gpurun_out/${TAG}_aux_10M.ncu-rep ] && python scripts/ncu_summary.py gpurun_out/${TAG}_aux_10M.ncu-rep > profiles/${TAG}_aux_kernels_10M_summary.txt
 [ -f gpurun_out/${TAG}_launches_B.csv ] && cp gpurun_out/${TAG}_launches_B.csv profiles/${TAG}_launches_B.csv
 python scripts/sass_opcodes.py > profiles/${TAG}_sass_opcodes.txt
+python scripts/ncu_traffic.py $TAG > /dev/null
