@@ -130,3 +130,57 @@ def test_compressed_fuzz(engine):
             index.set_option(name, int(rng.choice(choices)))
         _check(index, indptr, indices, data_q, n_docs, q, k)
         index.close()
+
+
+def test_compress_edge_cases(engine):
+    """Empty index, non-positive weights (general path) and weights that round to zero in bf16."""
+    # no postings at all
+    idx = engine.DeviceIndex(np.zeros(4, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32), n_docs=5).compress()
+    ids, sc = idx.search(np.array([[0, 2]], np.int32), 3)
+    assert ids.tolist() == [[0, 1, 2]] and sc.tolist() == [[0.0, 0.0, 0.0]]
+    idx.close()
+    rng = np.random.default_rng(5)
+    n_docs, n_terms = 9000, 12
+    cols = [np.sort(rng.choice(n_docs, size=int(rng.integers(1, 4000)), replace=False)).astype(np.int32) for _ in range(n_terms)]
+    indptr = np.concatenate([[0], np.cumsum([len(c) for c in cols])]).astype(np.int32)
+    indices = np.concatenate(cols)
+    q = rng.integers(-1, n_terms, size=(6, 5)).astype(np.int32)
+    # (a) mixed-sign weights: the general path of a compressed handle
+    data = rng.standard_normal(len(indices)).astype(np.float32)
+    h = engine.DeviceIndex(indptr, indices, data, n_docs=n_docs).compress()
+    assert h.info.all_positive == 0
+    _check(h, indptr, indices, engine.round_to_bf16(data), n_docs, q, 50)
+    h.close()
+    # (b) positive weights some of which round to +0.0 in bf16 (fp32 denormals): the handle must notice
+    data = (0.05 + rng.random(len(indices))).astype(np.float32)
+    data[::7] = np.float32(1e-45)
+    h = engine.DeviceIndex(indptr, indices, data, n_docs=n_docs)
+    assert h.info.all_positive == 1
+    h.compress()
+    dq = engine.round_to_bf16(data)
+    assert (dq == 0).any() and h.info.all_positive == 0
+    _check(h, indptr, indices, dq, n_docs, q, 50)
+    h.close()
+
+
+def test_alternating_query_shapes_on_one_handle(engine):
+    """Narrow queries run on 2048-document tiles, 64-term queries on 1792-document tiles (launch plan);
+    one handle keeps both tile tables (and both packed arrays) and answers both shapes, interleaved."""
+    from mojo_bm25_b200 import synth
+
+    idx, q4, _ = synth.make_workload("B", scale=0.2)
+    indptr, indices, data = idx.numpy()
+    q4 = q4.numpy()[:16]
+    rng = np.random.default_rng(9)
+    q64 = rng.integers(0, idx.n_terms, size=(8, 64)).astype(np.int32)
+    q64[:, :4] = rng.integers(0, 50, size=(8, 4))  # a few stop-word-length lists
+    for compress in (False, True):
+        h = engine.DeviceIndex(indptr, indices, data, n_docs=idx.n_docs)
+        dq = data
+        if compress:
+            h.compress()
+            dq = engine.round_to_bf16(data)
+        for _ in range(3):
+            _check(h, indptr, indices, dq, idx.n_docs, q4, 10)
+            _check(h, indptr, indices, dq, idx.n_docs, q64, 300)
+        h.close()
