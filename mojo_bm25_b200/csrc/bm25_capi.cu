@@ -975,6 +975,13 @@ int bm25_index_compress(bm25_index* ix, int weight_format) {
     if (ix->weight_format == weight_format) return BM25_OK;
     CU(cudaDeviceSynchronize());  // no search may still be reading the weights
     if (ix->n_terms > 0 && ix->nnz > 0) {
+        // nothing is modified unless every weight stays finite in bf16 (largest finite bf16: 0x7f7f0000)
+        std::vector<float2> wr((size_t)ix->n_terms);
+        CU(cudaMemcpy(wr.data(), ix->d_wrange, wr.size() * sizeof(float2), cudaMemcpyDeviceToHost));
+        const float lim = 3.3895313892515355e38f;
+        for (int64_t t = 0; t < ix->n_terms; ++t)
+            if (wr[t].y >= wr[t].x && (wr[t].y > lim || wr[t].x < -lim))
+                return fail(BM25_ERR_INVALID, "term %lld holds a weight that overflows bf16; the handle is unchanged", (long long)t);
         unsigned long long* d_flags = nullptr;
         unsigned long long h_flags[2] = {0, 0};
         CU(cudaMalloc(&d_flags, sizeof h_flags));

@@ -184,3 +184,16 @@ def test_alternating_query_shapes_on_one_handle(engine):
             _check(h, indptr, indices, dq, idx.n_docs, q4, 10)
             _check(h, indptr, indices, dq, idx.n_docs, q64, 300)
         h.close()
+
+
+def test_compress_refuses_weights_that_overflow_bf16_and_leaves_the_handle_intact(engine):
+    indptr = np.array([0, 2, 3], np.int32)
+    indices = np.array([0, 1, 1], np.int32)
+    data = np.array([1.0, 3.4e38, 2.0], np.float32)  # 3.4e38 rounds to +inf in bf16
+    h = engine.DeviceIndex(indptr, indices, data, n_docs=2)
+    with pytest.raises(ValueError):
+        h.compress()
+    assert h.info.weight_format == 0
+    ids, sc = h.search(np.array([[0, 1]], np.int32), 2)
+    assert ids.tolist() == [[1, 0]] and np.array_equal(sc, np.array([[np.float32(3.4e38) + np.float32(2.0), 1.0]], np.float32))
+    h.close()
