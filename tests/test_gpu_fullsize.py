@@ -50,6 +50,19 @@ def test_10m_target_config_full_size_k100_and_k10_prefix():
     ids10, sc10 = index.search_device(q, 10)
     torch.cuda.synchronize()
     assert np.array_equal(ids10.cpu().numpy(), ids[:, :10]) and np.array_equal(sc10.cpu().numpy(), sc[:, :10])
+    # the same handle compressed (4-byte postings, bf16 weights): the oracle on the rounded matrix
+    from mojo_bm25_b200 import engine
+
+    index.compress("bf16")
+    cids, csc = index.search_device(q, 100)
+    torch.cuda.synchronize()
+    cids, csc, qn = cids.cpu().numpy(), csc.cpu().numpy(), q.cpu().numpy()
+    assert np.all(csc[:, :-1] >= csc[:, 1:])
+    indptr, indices, data = idx.numpy()
+    data_q = engine.round_to_bf16(data)
+    for i in range(0, len(qn), len(qn) // 8)[:8]:
+        dense = c_oracle.scores_dense(indptr, indices, data_q, idx.n_docs, qn[i])
+        orc.check_topk_against_dense(cids[i], csc[i], dense, 100, exact=True)
 
 
 def test_config_d_one_full_shard_with_doc_id_base():
